@@ -1,0 +1,565 @@
+// Bandwidth-bound kernels around the codeword search: operand preparation, exact fp32 re-score +
+// gather + straight-through + commitment loss, EMA statistics, EMA finalize + dead-code reset,
+// backward, k-means mean update, perplexity.  All are warp-per-row kernels with 16-byte
+// coalesced accesses; roofline = HBM.
+//
+// Reference semantics: vector_quantize_pytorch.VectorQuantize as configured at
+// models/vq_brain.py:184-193 (restated in oracle/vector_quantize_ref.py).
+#include "common.cuh"
+
+namespace fk {
+
+constexpr int kRowsPerBlock = 8;   // 8 warps, one row each
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+
+// ------------------------------------------------------------------------------------------
+// K0: input transform.  cosine: xn = e / max(|e|, 1e-12) (F.normalize); Euclidean: xn = e.
+// Writes the fp32 row (if xn != null), the zero-padded bf16 row for the tensor cores and 1/|e|.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+vq_prepare_input_kernel(const T* __restrict__ e, long long N, int D, int Dp, int cosine, float* __restrict__ xn,
+                        __nv_bfloat16* __restrict__ xb, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const T* er = e + row * D;
+  float denom = 1.f;
+  if (cosine) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = to_f(er[d]); ss += v * v; }
+    ss = warp_sum(ss);
+    denom = fmaxf(sqrtf(ss), 1e-12f);   // F.normalize: x / max(|x|, eps)
+    if (lane == 0 && inv_norm) inv_norm[row] = 1.f / denom;
+  }
+  for (int d = lane; d < Dp; d += 32) {
+    float v = 0.f;
+    if (d < D) {
+      v = cosine ? to_f(er[d]) / denom : to_f(er[d]);
+      if (xn) xn[row * D + d] = v;
+    }
+    xb[row * Dp + d] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// codebook operand: bf16 copy (zero padded to Dp) and c2 = |bf16(c)|^2 (Euclidean) / 0 (cosine),
+// padded with +inf up to Kpad.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+vq_prepare_codebook_kernel(const float* __restrict__ embed, int K, int D, int Dp, int Kpad, int cosine,
+                           __nv_bfloat16* __restrict__ cb, float* __restrict__ c2pad) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (k >= Kpad) return;
+  if (k >= K) {
+    if (lane == 0) c2pad[k] = __int_as_float(0x7f800000);
+    return;
+  }
+  float ss = 0.f;
+  for (int d = lane; d < Dp; d += 32) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(d < D ? embed[static_cast<long long>(k) * D + d] : 0.f);
+    cb[static_cast<long long>(k) * Dp + d] = b;
+    const float f = __bfloat162float(b);
+    ss += f * f;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) c2pad[k] = cosine ? 0.f : ss;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2-K4: merge the candidate slots of a row to the approximate top-2, re-score both in exact
+// fp32 with the reference's formula, pick with lowest-index tie-break, gather the fp32 codeword,
+// straight-through output, commitment-loss partial sums.
+//   Euclidean (upstream cdist): d = sqrt(max(|x|^2 + |c|^2 - 2 x.c, 0)), minimise
+//   cosine                    : s = x.c, maximise
+// ------------------------------------------------------------------------------------------
+struct FinishParams {
+  const float* xn;       // [N, D]
+  const float* embed;    // [K, D]
+  const float* cand_val; // [N, S, 2]
+  const int* cand_idx;   // [N, S, 2]
+  long long* indices;    // [N]
+  float* quantize;       // [N, D]
+  float* partials;       // [gridDim.x]
+  unsigned int* counter; // zero on entry, zero on exit
+  float* loss;           // [1]
+  long long N;
+  int K, D, S, cosine, training;
+  float loss_scale;      // commitment_weight / (N * D)
+};
+
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+vq_finish_kernel(const FinishParams p) {
+  __shared__ float red[32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5);
+  float sq_err = 0.f;
+  if (row < p.N) {
+    // ---- approximate top-2 over the slots (every lane computes the same thing) ----
+    float b1 = __int_as_float(0x7f800000), b2 = b1;
+    int i1 = -1, i2 = -1;
+    for (int s = 0; s < p.S * 2; ++s) {
+      const int j = p.cand_idx[row * p.S * 2 + s];
+      const float v = p.cand_val[row * p.S * 2 + s];
+      if (j < 0 || j >= p.K) continue;
+      // order by (value, index): slots come from disjoint code ranges in ascending order, but be explicit
+      const bool lt1 = (v < b1) || (v == b1 && j < i1) || i1 < 0;
+      const bool lt2 = (v < b2) || (v == b2 && j < i2) || i2 < 0;
+      if (lt1) { b2 = b1; i2 = i1; b1 = v; i1 = j; }
+      else if (lt2) { b2 = v; i2 = j; }
+    }
+    if (i1 < 0) i1 = 0;          // all-NaN row: no candidate survived a comparison
+    // ---- exact fp32 scores ----
+    const float* xr = p.xn + row * p.D;
+    const float* c1 = p.embed + static_cast<long long>(i1) * p.D;
+    const float* c2 = p.embed + static_cast<long long>(i2 < 0 ? i1 : i2) * p.D;
+    float xx = 0.f, d1 = 0.f, d2 = 0.f, n1 = 0.f, n2 = 0.f;
+    for (int d = lane * 4; d < p.D; d += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(xr + d);
+      const float4 a = *reinterpret_cast<const float4*>(c1 + d);
+      const float4 b = *reinterpret_cast<const float4*>(c2 + d);
+      xx += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+      d1 += x.x * a.x + x.y * a.y + x.z * a.z + x.w * a.w;
+      d2 += x.x * b.x + x.y * b.y + x.z * b.z + x.w * b.w;
+      n1 += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+      n2 += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    }
+    xx = warp_sum(xx); d1 = warp_sum(d1); d2 = warp_sum(d2); n1 = warp_sum(n1); n2 = warp_sum(n2);
+    int best = i1;
+    if (i2 >= 0) {
+      bool second_wins;
+      if (p.cosine) {
+        second_wins = (d2 > d1) || (d2 == d1 && i2 < i1);
+      } else {
+        const float e1 = sqrtf(fmaxf(xx + n1 - 2.f * d1, 0.f));
+        const float e2 = sqrtf(fmaxf(xx + n2 - 2.f * d2, 0.f));
+        second_wins = (e2 < e1) || (e2 == e1 && i2 < i1);
+      }
+      if (second_wins) best = i2;
+    }
+    const float* cq = (best == i1) ? c1 : c2;
+    if (lane == 0) p.indices[row] = best;
+    float* qr = p.quantize + row * p.D;
+    for (int d = lane * 4; d < p.D && p.quantize != nullptr; d += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(xr + d);
+      const float4 q = *reinterpret_cast<const float4*>(cq + d);
+      float4 o;
+      if (p.training) {
+        // straight-through value x + (q - x), rounded exactly like the reference expression
+        const float ex = q.x - x.x, ey = q.y - x.y, ez = q.z - x.z, ew = q.w - x.w;
+        o = make_float4(x.x + ex, x.y + ey, x.z + ez, x.w + ew);
+        sq_err += ex * ex + ey * ey + ez * ez + ew * ew;
+      } else {
+        o = q;
+      }
+      *reinterpret_cast<float4*>(qr + d) = o;
+    }
+  }
+  if (!p.training) return;
+  // ---- commitment loss: deterministic two-level reduction (block partials, last block sums) ----
+  const float bsum = block_sum(sq_err, red);
+  if (threadIdx.x == 0) {
+    p.partials[blockIdx.x] = bsum;
+    __threadfence();
+    const unsigned int done = atomicAdd(p.counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float acc = 0.f;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) acc += __ldcg(p.partials + i);
+    const float total = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      p.loss[0] = total * p.loss_scale;
+      *p.counter = 0u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: EMA statistics.  stats = [K*D embed_sum | K bins] (one packed buffer = one all-reduce).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+vq_ema_stats_kernel(const float* __restrict__ xn, const long long* __restrict__ indices, long long N, int K, int D,
+                    float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const long long k = indices[row];
+  if (k < 0 || k >= K) return;
+  const float* xr = xn + row * D;
+  float* dst = stats + k * D;
+  for (int d = lane * 4; d < D; d += 128) {
+    const float4 x = *reinterpret_cast<const float4*>(xr + d);
+    atomicAdd(reinterpret_cast<float4*>(dst + d), x);   // one 16-byte reduction at L2
+  }
+  if (lane == 0) atomicAdd(stats + static_cast<long long>(K) * D + k, 1.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// K6a: cluster_size EMA, its total, expired flags and their ranks (single block, K <= 2^20).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+vq_ema_cluster_kernel(const float* __restrict__ bins, float* __restrict__ cluster_size, int K, float decay,
+                      float threshold, float* __restrict__ total_out, int* __restrict__ expire_rank,
+                      int* __restrict__ n_expired) {
+  __shared__ float red[32];
+  __shared__ int scan[1024];
+  const int per = (K + blockDim.x - 1) / blockDim.x;
+  const int k0 = threadIdx.x * per, k1 = min(K, k0 + per);
+  float sum = 0.f;
+  int cnt = 0;
+  for (int k = k0; k < k1; ++k) {
+    const float cs = cluster_size[k];
+    const float nv = cs + (1.f - decay) * (bins[k] - cs);   // torch lerp_(end, weight), weight < 0.5
+    cluster_size[k] = nv;
+    sum += nv;
+    cnt += (nv < threshold) ? 1 : 0;
+  }
+  const float total = block_sum(sum, red);
+  if (threadIdx.x == 0) *total_out = total;
+  // exclusive scan of per-thread expired counts
+  scan[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int off = 1; off < blockDim.x; off <<= 1) {
+    const int v = (threadIdx.x >= off) ? scan[threadIdx.x - off] : 0;
+    __syncthreads();
+    scan[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int rank = scan[threadIdx.x] - cnt;
+  if (threadIdx.x == blockDim.x - 1) *n_expired = scan[threadIdx.x];
+  for (int k = k0; k < k1; ++k) {
+    const bool ex = cluster_size[k] < threshold;
+    expire_rank[k] = ex ? rank : -1;
+    rank += ex ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6b: embed_avg EMA, Laplace-smoothed normalisation, (cosine) l2norm, dead-code replacement,
+// and the next step's tensor-core operand (bf16 codebook + c2).  One warp per code.
+// ------------------------------------------------------------------------------------------
+struct EmaParams {
+  const float* stats;        // [K*D | K] (already all-reduced)
+  float* cluster_size;       // [K]  (already EMA-updated by K6a)
+  float* embed_avg;          // [K, D]
+  float* embed;              // [K, D]
+  const float* total;        // [1]
+  const int* expire_rank;    // [K]
+  const long long* sample_rows;   // [n_sample] rows of xn used for dead-code replacement (may be null)
+  const float* xn;           // [N, D]
+  __nv_bfloat16* cb;         // [K, Dp]
+  float* c2pad;              // [Kpad]
+  long long N;
+  int K, D, Dp, Kpad, cosine, n_sample;
+  float decay, eps, threshold;
+};
+
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+vq_ema_update_kernel(const EmaParams p) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (k >= p.Kpad) return;
+  if (k >= p.K) {
+    if (lane == 0) p.c2pad[k] = __int_as_float(0x7f800000);
+    return;
+  }
+  const long long base = static_cast<long long>(k) * p.D;
+  const int rank = p.expire_rank[k];
+  const bool expired = rank >= 0 && p.sample_rows != nullptr && p.n_sample > 0;
+  float ss = 0.f;
+  if (!expired) {
+    const float total = *p.total;
+    const float cs = p.cluster_size[k];
+    // laplace_smoothing(cs, K, eps) * total
+    const float smoothed = (cs + p.eps) / (total + p.K * p.eps) * total;
+    for (int d = lane; d < p.D; d += 32) {
+      const float avg = p.embed_avg[base + d];
+      const float nv = avg + (1.f - p.decay) * (p.stats[base + d] - avg);
+      p.embed_avg[base + d] = nv;
+      const float e = nv / smoothed;
+      p.embed[base + d] = e;
+      ss += e * e;
+    }
+    if (p.cosine) {
+      ss = warp_sum(ss);
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+      for (int d = lane; d < p.D; d += 32) p.embed[base + d] = p.embed[base + d] / nrm;
+    }
+  } else {
+    // upstream expire_codes_/replace: embed <- sampled row (l2norm'd for cosine), embed_avg <- row * thr,
+    // cluster_size <- thr.  The EMA of embed_avg for this code is overwritten, as in the reference.
+    const long long r = p.sample_rows[rank % p.n_sample];
+    const float* xr = p.xn + r * p.D;
+    float nrm = 1.f;
+    if (p.cosine) {
+      float s2 = 0.f;
+      for (int d = lane; d < p.D; d += 32) s2 += xr[d] * xr[d];
+      s2 = warp_sum(s2);
+      nrm = fmaxf(sqrtf(s2), 1e-12f);
+    }
+    for (int d = lane; d < p.D; d += 32) {
+      const float v = p.cosine ? xr[d] / nrm : xr[d];
+      p.embed[base + d] = v;
+      p.embed_avg[base + d] = v * p.threshold;
+    }
+    if (lane == 0) p.cluster_size[k] = p.threshold;
+  }
+  __syncwarp();
+  // operand for the next search
+  float s2 = 0.f;
+  for (int d = lane; d < p.Dp; d += 32) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(d < p.D ? p.embed[base + d] : 0.f);
+    p.cb[static_cast<long long>(k) * p.Dp + d] = b;
+    const float f = __bfloat162float(b);
+    s2 += f * f;
+  }
+  s2 = warp_sum(s2);
+  if (lane == 0) p.c2pad[k] = p.cosine ? 0.f : s2;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: dL/dx = g_out + g_loss * (2 w / (N D)) * (x - q); cosine chains through F.normalize:
+// dL/de = (g - x (x.g)) / max(|e|, eps).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+vq_backward_kernel(const float* __restrict__ g_out, const float* __restrict__ g_loss, const float* __restrict__ xn,
+                   const float* __restrict__ q, const float* __restrict__ inv_norm, long long N, int D, int cosine,
+                   float coef, float* __restrict__ ge) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float gl = g_loss ? g_loss[0] * coef : 0.f;
+  const long long base = row * D;
+  float dot = 0.f;
+  if (cosine) {
+    for (int d = lane * 4; d < D; d += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(xn + base + d);
+      const float4 qq = *reinterpret_cast<const float4*>(q + base + d);
+      float4 g = g_out ? *reinterpret_cast<const float4*>(g_out + base + d) : make_float4(0, 0, 0, 0);
+      g.x += gl * (x.x - qq.x); g.y += gl * (x.y - qq.y); g.z += gl * (x.z - qq.z); g.w += gl * (x.w - qq.w);
+      dot += g.x * x.x + g.y * x.y + g.z * x.z + g.w * x.w;
+    }
+    dot = warp_sum(dot);
+  }
+  const float inv = cosine ? inv_norm[row] : 1.f;
+  for (int d = lane * 4; d < D; d += 128) {
+    const float4 x = *reinterpret_cast<const float4*>(xn + base + d);
+    const float4 qq = *reinterpret_cast<const float4*>(q + base + d);
+    float4 g = g_out ? *reinterpret_cast<const float4*>(g_out + base + d) : make_float4(0, 0, 0, 0);
+    g.x += gl * (x.x - qq.x); g.y += gl * (x.y - qq.y); g.z += gl * (x.z - qq.z); g.w += gl * (x.w - qq.w);
+    if (cosine) {
+      g.x = (g.x - x.x * dot) * inv; g.y = (g.y - x.y * dot) * inv;
+      g.z = (g.z - x.z * dot) * inv; g.w = (g.w - x.w * dot) * inv;
+    }
+    *reinterpret_cast<float4*>(ge + base + d) = g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k-means mean update (upstream `kmeans`): new = sum / max(bins, 1) (cosine: l2norm), keep the
+// old mean where bins == 0.  Also refreshes the tensor-core operand.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+vq_kmeans_update_kernel(const float* __restrict__ stats, float* __restrict__ means, int K, int D, int Dp, int Kpad,
+                        int cosine, __nv_bfloat16* __restrict__ cb, float* __restrict__ c2pad) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (k >= Kpad) return;
+  if (k >= K) {
+    if (lane == 0) c2pad[k] = __int_as_float(0x7f800000);
+    return;
+  }
+  const long long base = static_cast<long long>(k) * D;
+  const float bins = stats[static_cast<long long>(K) * D + k];
+  if (bins != 0.f) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float v = stats[base + d] / bins;
+      means[base + d] = v;
+      ss += v * v;
+    }
+    if (cosine) {
+      ss = warp_sum(ss);
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+      for (int d = lane; d < D; d += 32) means[base + d] = means[base + d] / nrm;
+    }
+  }
+  __syncwarp();
+  float s2 = 0.f;
+  for (int d = lane; d < Dp; d += 32) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(d < D ? means[base + d] : 0.f);
+    cb[static_cast<long long>(k) * Dp + d] = b;
+    const float f = __bfloat162float(b);
+    s2 += f * f;
+  }
+  s2 = warp_sum(s2);
+  if (lane == 0) c2pad[k] = cosine ? 0.f : s2;
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: perplexity from the code histogram (models/vq_brain.py:238-243): exp(-sum p log(p + 1e-10)).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+vq_perplexity_kernel(const float* __restrict__ bins, int K, float inv_n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float pk = bins[k] * inv_n;
+    acc += pk * logf(pk + 1e-10f);
+  }
+  const float s = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = expf(-s);
+}
+
+__global__ void __launch_bounds__(256)
+vq_histogram_kernel(const long long* __restrict__ indices, long long N, int K, float* __restrict__ bins) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const long long k = indices[i];
+  if (k >= 0 && k < K) atomicAdd(bins + k, 1.f);
+}
+
+}  // namespace fk
+
+using namespace fk;
+
+static inline unsigned row_blocks(long long rows) { return static_cast<unsigned>((rows + kRowsPerBlock - 1) / kRowsPerBlock); }
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_prepare_input(const void* e, int dtype, long long N, int D, int Dp, int use_cosine, float* xn,
+                                   void* x_bf16, float* inv_norm, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(N > 0 && D > 0 && Dp >= D, "fk_vq_prepare_input: bad shape");
+  FK_REQUIRE(e && x_bf16, "fk_vq_prepare_input: null pointer");
+  FK_REQUIRE(!use_cosine || inv_norm, "fk_vq_prepare_input: cosine needs inv_norm");
+  auto* xb = static_cast<__nv_bfloat16*>(x_bf16);
+  switch (dtype) {
+    case 0: vq_prepare_input_kernel<float><<<row_blocks(N), kRowsPerBlock * 32, 0, stream>>>(
+                static_cast<const float*>(e), N, D, Dp, use_cosine, xn, xb, inv_norm); break;
+    case 1: vq_prepare_input_kernel<__nv_bfloat16><<<row_blocks(N), kRowsPerBlock * 32, 0, stream>>>(
+                static_cast<const __nv_bfloat16*>(e), N, D, Dp, use_cosine, xn, xb, inv_norm); break;
+    case 2: vq_prepare_input_kernel<__half><<<row_blocks(N), kRowsPerBlock * 32, 0, stream>>>(
+                static_cast<const __half*>(e), N, D, Dp, use_cosine, xn, xb, inv_norm); break;
+    default: FK_REQUIRE(false, "fk_vq_prepare_input: dtype must be 0 (f32), 1 (bf16) or 2 (f16)");
+  }
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_prepare_codebook(const float* embed, int K, int D, int Dp, int Kpad, int use_cosine, void* cb_bf16,
+                                      float* c2pad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(K > 0 && D > 0 && Dp >= D && Kpad >= K, "fk_vq_prepare_codebook: bad shape");
+  FK_REQUIRE(embed && cb_bf16 && c2pad, "fk_vq_prepare_codebook: null pointer");
+  vq_prepare_codebook_kernel<<<row_blocks(Kpad), kRowsPerBlock * 32, 0, stream>>>(
+      embed, K, D, Dp, Kpad, use_cosine, static_cast<__nv_bfloat16*>(cb_bf16), c2pad);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_finish(const float* xn, const float* embed, const float* cand_val, const int* cand_idx, long long N,
+                            int K, int D, int S, int use_cosine, int training, float commitment_weight,
+                            long long* indices, float* quantize, float* loss, float* partials, unsigned int* counter,
+                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(N > 0 && K > 0 && D > 0 && S > 0, "fk_vq_finish: bad shape");
+  FK_REQUIRE(D % 4 == 0, "fk_vq_finish: D must be a multiple of 4");
+  FK_REQUIRE(xn && embed && cand_val && cand_idx && indices, "fk_vq_finish: null pointer");
+  FK_REQUIRE(quantize || !training, "fk_vq_finish: training needs the quantize output");
+  FK_REQUIRE(!training || (loss && partials && counter), "fk_vq_finish: training needs loss/partials/counter");
+  FinishParams p;
+  p.xn = xn; p.embed = embed; p.cand_val = cand_val; p.cand_idx = cand_idx;
+  p.indices = indices; p.quantize = quantize; p.partials = partials; p.counter = counter; p.loss = loss;
+  p.N = N; p.K = K; p.D = D; p.S = S; p.cosine = use_cosine; p.training = training;
+  p.loss_scale = static_cast<float>(static_cast<double>(commitment_weight) / (static_cast<double>(N) * D));
+  vq_finish_kernel<<<row_blocks(N), kRowsPerBlock * 32, 0, stream>>>(p);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) long long fk_vq_finish_partials(long long N) { return (N + kRowsPerBlock - 1) / kRowsPerBlock; }
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_ema_stats(const float* xn, const long long* indices, long long N, int K, int D, float* stats,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(N > 0 && K > 0 && D > 0 && D % 4 == 0, "fk_vq_ema_stats: bad shape (D % 4 == 0)");
+  FK_REQUIRE(xn && indices && stats, "fk_vq_ema_stats: null pointer");
+  if (cudaMemsetAsync(stats, 0, (static_cast<size_t>(K) * D + K) * sizeof(float), stream) != cudaSuccess) return FK_ERR_CUDA;
+  vq_ema_stats_kernel<<<row_blocks(N), kRowsPerBlock * 32, 0, stream>>>(xn, indices, N, K, D, stats);
+  FK_CHECK_LAUNCH();
+  fk_count_launch(2);
+  return FK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_ema_update(const float* stats, float* cluster_size, float* embed_avg, float* embed, int K, int D,
+                                int Dp, int Kpad, int use_cosine, float decay, float eps, float threshold,
+                                const long long* sample_rows, int n_sample, const float* xn, long long N, void* cb_bf16,
+                                float* c2pad, float* total_ws, int* expire_rank_ws, int* n_expired, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(K > 0 && K <= (1 << 20) && D > 0 && Dp >= D && Kpad >= K, "fk_vq_ema_update: bad shape");
+  FK_REQUIRE(stats && cluster_size && embed_avg && embed && cb_bf16 && c2pad && total_ws && expire_rank_ws && n_expired,
+             "fk_vq_ema_update: null pointer");
+  FK_REQUIRE(threshold <= 0.f || sample_rows == nullptr || (xn && n_sample > 0 && N > 0),
+             "fk_vq_ema_update: dead-code reset needs xn and sample rows");
+  vq_ema_cluster_kernel<<<1, 1024, 0, stream>>>(stats + static_cast<long long>(K) * D, cluster_size, K, decay, threshold,
+                                               total_ws, expire_rank_ws, n_expired);
+  FK_CHECK_LAUNCH();
+  EmaParams p;
+  p.stats = stats; p.cluster_size = cluster_size; p.embed_avg = embed_avg; p.embed = embed; p.total = total_ws;
+  p.expire_rank = expire_rank_ws; p.sample_rows = (threshold > 0.f) ? sample_rows : nullptr; p.xn = xn;
+  p.cb = static_cast<__nv_bfloat16*>(cb_bf16); p.c2pad = c2pad; p.N = N; p.K = K; p.D = D; p.Dp = Dp; p.Kpad = Kpad;
+  p.cosine = use_cosine; p.n_sample = n_sample; p.decay = decay; p.eps = eps; p.threshold = threshold;
+  vq_ema_update_kernel<<<row_blocks(Kpad), kRowsPerBlock * 32, 0, stream>>>(p);
+  FK_CHECK_LAUNCH();
+  fk_count_launch(2);
+  return FK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_backward(const float* g_out, const float* g_loss, const float* xn, const float* quantize,
+                              const float* inv_norm, long long N, int D, int use_cosine, float commitment_weight,
+                              float* grad_in, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(N > 0 && D > 0 && D % 4 == 0, "fk_vq_backward: bad shape (D % 4 == 0)");
+  FK_REQUIRE(xn && quantize && grad_in, "fk_vq_backward: null pointer");
+  FK_REQUIRE(!use_cosine || inv_norm, "fk_vq_backward: cosine needs inv_norm");
+  const float coef = static_cast<float>(2.0 * commitment_weight / (static_cast<double>(N) * D));
+  vq_backward_kernel<<<row_blocks(N), kRowsPerBlock * 32, 0, stream>>>(g_out, g_loss, xn, quantize, inv_norm, N, D,
+                                                                       use_cosine, coef, grad_in);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_kmeans_update(const float* stats, float* means, int K, int D, int Dp, int Kpad, int use_cosine,
+                                   void* cb_bf16, float* c2pad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(K > 0 && D > 0 && Dp >= D && Kpad >= K, "fk_vq_kmeans_update: bad shape");
+  FK_REQUIRE(stats && means && cb_bf16 && c2pad, "fk_vq_kmeans_update: null pointer");
+  vq_kmeans_update_kernel<<<row_blocks(Kpad), kRowsPerBlock * 32, 0, stream>>>(
+      stats, means, K, D, Dp, Kpad, use_cosine, static_cast<__nv_bfloat16*>(cb_bf16), c2pad);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_perplexity(const long long* indices, long long N, int K, float* bins_ws, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(N > 0 && K > 0 && indices && bins_ws && out, "fk_vq_perplexity: bad argument");
+  if (cudaMemsetAsync(bins_ws, 0, static_cast<size_t>(K) * sizeof(float), stream) != cudaSuccess) return FK_ERR_CUDA;
+  vq_histogram_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, stream>>>(indices, N, K, bins_ws);
+  FK_CHECK_LAUNCH();
+  vq_perplexity_kernel<<<1, 1024, 0, stream>>>(bins_ws, K, 1.f / static_cast<float>(N), out);
+  FK_CHECK_LAUNCH();
+  fk_count_launch(3);
+  return FK_OK;
+}

@@ -1,0 +1,401 @@
+// Nearest-codeword search: S = X * C^T on the 5th-gen tensor cores (tcgen05.mma, bf16 operands,
+// fp32 accumulators in TMEM), operands staged by TMA, and the per-row arg-extremum taken in the
+// epilogue straight out of TMEM -- the [N, K] similarity matrix never exists in memory.
+//
+// Replaces (reference call site models/vq_brain.py:209 -> vector_quantize_pytorch
+// EuclideanCodebook/CosineSimCodebook.forward): `dist = -cdist(x, embed)` / `einsum('h n d, h c d -> h n c')`
+// followed by `dist.argmax(-1)`; SURVEY.md section 2a rows K1+K2.
+//
+// Score convention: the kernel MINIMISES  v[n][k] = alpha * (x_n . c_k) + c2[k]
+//   Euclidean: alpha = -2, c2[k] = |c_k|^2   (|x|^2 is row-constant, sqrt/clamp are monotone)
+//   cosine   : alpha = -1, c2[k] = 0         (argmax of the similarity)
+// c2 is padded to a multiple of BN with +inf so that out-of-range codes can never win.
+// Because bf16 operands perturb near-ties, the kernel keeps the TOP-2 (value, index) per row per
+// work segment; fk_vq_finish re-scores those candidates in exact fp32 and applies the reference's
+// tie rule (lowest index wins).
+//
+// Tiling: CTA tile = 256 rows (two M=128 accumulators) x 128 codes, K-depth = D (<= 256, whole
+// depth resident for X).  A work unit is one (row block, code tile) pair; the W = RB*T units are
+// cut into gridDim.x contiguous ranges (persistent CTAs, perfect balance to within one unit), so a
+// CTA covers at most a few row blocks ("segments") and writes one candidate slot per segment.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 =
+// TMEM allocator, warps 4-7 / 8-11 = epilogue for accumulator rows 0-127 / 128-255.
+#include "common.cuh"
+
+namespace fk {
+
+constexpr int kBM = 256;          // rows per CTA tile (2 x UMMA_M)
+constexpr int kBN = 128;          // codes per tile (UMMA_N)
+constexpr int kSlabK = 64;        // bf16 elements per 128-byte swizzled row
+constexpr int kXSlabBytes = kBM * 128;   // 32 KB
+constexpr int kBSlabBytes = kBN * 128;   // 16 KB
+constexpr int kSearchThreads = 384;
+constexpr int kMaxStages = 8;
+
+struct SearchParams {
+  const float* c2pad;   // [T * kBN]
+  float* cand_val;      // [N][S][2]
+  int* cand_idx;        // [N][S][2]
+  float* dbg_scores;    // optional [N][T*kBN] raw accumulators (tests only)
+  long long N;
+  int K, nslab, T, RB, S, nstage;
+  float alpha;
+};
+
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&r)[32]) {
+  // tcgen05.wait::ld with the destination registers as in/out operands, so that no use of r[] can
+  // be scheduled above the wait.
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+
+struct Top2 {
+  float b1, b2;
+  int i1, i2;
+  __device__ __forceinline__ void update(float v, int j) {
+    const bool p1 = v < b1, p2 = v < b2;
+    i2 = p1 ? i1 : (p2 ? j : i2);
+    b2 = p1 ? b1 : (p2 ? v : b2);
+    i1 = p1 ? j : i1;
+    b1 = p1 ? v : b1;
+  }
+};
+
+// 32 accumulator columns of this thread's row: chunk-of-8 minimum first (2 instr / element), the
+// index-tracking update only for chunks that can change the running top-2.
+__device__ __forceinline__ void scan32(const uint32_t (&r)[32], const float* c2s, float alpha, int jbase, Top2& t) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 ca = *reinterpret_cast<const float4*>(c2s + g * 8);
+    const float4 cb = *reinterpret_cast<const float4*>(c2s + g * 8 + 4);
+    float v[8];
+    v[0] = fmaf(__uint_as_float(r[g * 8 + 0]), alpha, ca.x);
+    v[1] = fmaf(__uint_as_float(r[g * 8 + 1]), alpha, ca.y);
+    v[2] = fmaf(__uint_as_float(r[g * 8 + 2]), alpha, ca.z);
+    v[3] = fmaf(__uint_as_float(r[g * 8 + 3]), alpha, ca.w);
+    v[4] = fmaf(__uint_as_float(r[g * 8 + 4]), alpha, cb.x);
+    v[5] = fmaf(__uint_as_float(r[g * 8 + 5]), alpha, cb.y);
+    v[6] = fmaf(__uint_as_float(r[g * 8 + 6]), alpha, cb.z);
+    v[7] = fmaf(__uint_as_float(r[g * 8 + 7]), alpha, cb.w);
+    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+    if (m < t.b2) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t.update(v[e], jbase + g * 8 + e);
+    }
+  }
+}
+
+__device__ __noinline__ void dump32(const uint32_t (&r)[32], float* dst) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kSearchThreads, 1)
+vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_c,
+                 const SearchParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle (TMA destination and UMMA descriptors).
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  uint8_t* smem = smem_raw;
+  uint8_t* Xs = smem;                                   // nslab x 32 KB
+  uint8_t* Bs = Xs + p.nslab * kXSlabBytes;             // nstage x 16 KB
+  float* c2s = reinterpret_cast<float*>(Bs + p.nstage * kBSlabBytes);   // [2][kBN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c2s + 2 * kBN);
+  uint64_t* full = bars;                    // [kMaxStages]
+  uint64_t* empty = bars + kMaxStages;      // [kMaxStages]
+  uint64_t* x_full = bars + 2 * kMaxStages;
+  uint64_t* x_empty = x_full + 1;
+  uint64_t* tmem_full = x_full + 2;         // [2]
+  uint64_t* tmem_empty = x_full + 4;        // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(x_full + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.nstage; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);   // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  // contiguous range of work units for this CTA
+  const long long W = static_cast<long long>(p.RB) * p.T;
+  const long long G = gridDim.x;
+  const long long u_begin = (static_cast<long long>(blockIdx.x) * W) / G;
+  const long long u_end = (static_cast<long long>(blockIdx.x + 1) * W) / G;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const int rb = static_cast<int>(u / p.T), t0 = static_cast<int>(u % p.T);
+        const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
+        mbar_wait(x_empty, (seg & 1) ^ 1);
+        mbar_expect_tx(x_full, p.nslab * kXSlabBytes);
+        for (int ks = 0; ks < p.nslab; ++ks) tma_load_2d(Xs + ks * kXSlabBytes, &tmap_x, x_full, ks * kSlabK, rb * kBM);
+        for (int t = t0; t < t0 + nt; ++t) {
+          for (int ks = 0; ks < p.nslab; ++ks) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], kBSlabBytes);
+            tma_load_2d(Bs + stage * kBSlabBytes, &tmap_c, &full[stage], ks * kSlabK, t * kBN);
+            if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+          }
+        }
+        u += nt;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kBN);
+      const uint32_t xs_addr = smem_u32(Xs), bs_addr = smem_u32(Bs);
+      int stage = 0;
+      uint32_t phase = 0, seg = 0, tc = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const int t0 = static_cast<int>(u % p.T);
+        const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
+        mbar_wait(x_full, seg & 1);
+        tc_fence_after();
+        for (int t = 0; t < nt; ++t, ++tc) {
+          const uint32_t as = tc & 1;
+          mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int ks = 0; ks < p.nslab; ++ks) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t d_tmem = tmem_base + (h * 2 + as) * kBN;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t adesc = umma_desc_sw128(xs_addr + ks * kXSlabBytes + h * (128 * 128) + kk * 32);
+                const uint64_t bdesc = umma_desc_sw128(bs_addr + stage * kBSlabBytes + kk * 32);
+                umma_bf16(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0);
+              }
+            }
+            umma_commit(&empty[stage]);   // slab free once these MMAs retire
+            if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[as]);
+        }
+        umma_commit(x_empty);
+        u += nt;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int h = (warp - 4) >> 2;          // accumulator half == warpgroup
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int tid128 = (warp - 4 - h * 4) * 32 + lane;
+    float* my_c2 = c2s + h * kBN;
+    uint32_t tc = 0;
+    for (long long u = u_begin; u < u_end;) {
+      const int rb = static_cast<int>(u / p.T), t0 = static_cast<int>(u % p.T);
+      const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
+      Top2 best;
+      best.b1 = best.b2 = __int_as_float(0x7f800000);
+      best.i1 = best.i2 = -1;
+      for (int t = t0; t < t0 + nt; ++t, ++tc) {
+        const uint32_t as = tc & 1;
+        named_bar_sync(1 + h, 128);                       // previous tile's c2 reads are done
+        my_c2[tid128] = __ldg(p.c2pad + static_cast<long long>(t) * kBN + tid128);
+        named_bar_sync(1 + h, 128);
+        mbar_wait(&tmem_full[as], (tc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (h * 2 + as) * kBN;
+        uint32_t ra[32], rb2[32];
+        const long long drow = static_cast<long long>(rb) * kBM + h * 128 + q * 32 + lane;
+        float* dbg = (p.dbg_scores != nullptr && drow < p.N)
+                         ? p.dbg_scores + drow * (static_cast<long long>(p.T) * kBN) + static_cast<long long>(t) * kBN
+                         : nullptr;
+        tmem_ld32(taddr, ra);
+        tmem_wait_ld_dep(ra);
+        tmem_ld32(taddr + 32, rb2);
+        if (dbg) dump32(ra, dbg);
+        scan32(ra, my_c2, p.alpha, t * kBN, best);
+        tmem_wait_ld_dep(rb2);
+        tmem_ld32(taddr + 64, ra);
+        if (dbg) dump32(rb2, dbg + 32);
+        scan32(rb2, my_c2 + 32, p.alpha, t * kBN + 32, best);
+        tmem_wait_ld_dep(ra);
+        tmem_ld32(taddr + 96, rb2);
+        if (dbg) dump32(ra, dbg + 64);
+        scan32(ra, my_c2 + 64, p.alpha, t * kBN + 64, best);
+        tmem_wait_ld_dep(rb2);
+        if (dbg) dump32(rb2, dbg + 96);
+        scan32(rb2, my_c2 + 96, p.alpha, t * kBN + 96, best);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      }
+      // candidate slot of this segment inside its row block
+      const long long ufirst = static_cast<long long>(rb) * p.T;
+      const int first_cta = static_cast<int>(((ufirst + 1) * G - 1) / W);
+      const int slot = static_cast<int>(blockIdx.x) - first_cta;
+      const long long row = static_cast<long long>(rb) * kBM + h * 128 + q * 32 + lane;
+      if (row < p.N && slot >= 0 && slot < p.S) {
+        const long long o = (row * p.S + slot) * 2;
+        *reinterpret_cast<float2*>(p.cand_val + o) = make_float2(best.b1, best.b2);
+        *reinterpret_cast<int2*>(p.cand_idx + o) = make_int2(best.i1, best.i2);
+      }
+      u += nt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// bf16 row-major [rows, cols] matrix, box = 64 columns x box_rows rows, 128-byte swizzle.
+int make_tmap_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return FK_ERR_DRIVER;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FK_OK : FK_ERR_DRIVER;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace fk
+
+using namespace fk;
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_search_slots(long long N, int K, int max_ctas) {
+  if (N <= 0 || K <= 0) return FK_ERR_BAD_ARG;
+  const long long RB = (N + kBM - 1) / kBM, T = (K + kBN - 1) / kBN, W = RB * T;
+  long long G = max_ctas > 0 ? max_ctas : 148;
+  if (G > W) G = W;
+  int S = 1;
+  for (long long rb = 0; rb < RB; ++rb) {
+    const long long first = ((rb * T + 1) * G - 1) / W;
+    const long long last = (((rb + 1) * T - 1 + 1) * G - 1) / W;
+    if (last - first + 1 > S) S = static_cast<int>(last - first + 1);
+  }
+  return S;
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                                  int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, float* dbg_scores,
+                                  void* stream_);
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_search(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                            int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, void* stream_) {
+  return fk_vq_search_debug(x_bf16, cb_bf16, c2pad, N, K, Dp, use_cosine, cand_val, cand_idx, S, max_ctas, nullptr, stream_);
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                                  int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, float* dbg_scores,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(N > 0 && K > 0, "fk_vq_search: empty problem");
+  FK_REQUIRE(Dp % 64 == 0 && Dp >= 64 && Dp <= 256, "fk_vq_search: padded dim must be 64, 128, 192 or 256");
+  FK_REQUIRE(x_bf16 && cb_bf16 && c2pad && cand_val && cand_idx, "fk_vq_search: null pointer");
+  const long long RB = (N + kBM - 1) / kBM, T = (K + kBN - 1) / kBN, W = RB * T;
+  FK_REQUIRE(RB < (1ll << 30) && T < (1 << 24), "fk_vq_search: problem too large");
+  long long G = max_ctas > 0 ? max_ctas : sm_count();
+  if (G > W) G = W;
+  FK_REQUIRE(S == fk_vq_search_slots(N, K, static_cast<int>(G)), "fk_vq_search: slot count does not match fk_vq_search_slots");
+
+  CUtensorMap tx, tcm;
+  int rc = make_tmap_bf16_sw128(&tx, x_bf16, static_cast<uint64_t>(N), static_cast<uint64_t>(Dp), kBM);
+  if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled(x) failed", __FILE__, __LINE__); return rc; }
+  rc = make_tmap_bf16_sw128(&tcm, cb_bf16, static_cast<uint64_t>(K), static_cast<uint64_t>(Dp), kBN);
+  if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled(codebook) failed", __FILE__, __LINE__); return rc; }
+
+  SearchParams p;
+  p.c2pad = c2pad;
+  p.cand_val = cand_val;
+  p.cand_idx = cand_idx;
+  p.dbg_scores = dbg_scores;
+  p.N = N;
+  p.K = K;
+  p.nslab = Dp / 64;
+  p.T = static_cast<int>(T);
+  p.RB = static_cast<int>(RB);
+  p.S = S;
+  p.alpha = use_cosine ? -1.f : -2.f;
+  const int fixed = p.nslab * kXSlabBytes + 2 * kBN * 4 + 256 /*barriers*/;
+  int nstage = (232448 - 1024 /*static*/ - fixed) / kBSlabBytes;
+  if (nstage > kMaxStages) nstage = kMaxStages;
+  p.nstage = nstage;
+  const int smem_bytes = fixed + nstage * kBSlabBytes;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(vq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess) {
+      fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
+      return FK_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  // unused slots must read as "no candidate"
+  if (cudaMemsetAsync(cand_idx, 0xFF, static_cast<size_t>(N) * S * 2 * sizeof(int), stream) != cudaSuccess) return FK_ERR_CUDA;
+  vq_search_kernel<<<static_cast<unsigned>(G), kSearchThreads, smem_bytes, stream>>>(tx, tcm, p);
+  FK_CHECK_LAUNCH();
+  fk_count_launch(2);
+  return FK_OK;
+}

@@ -1,0 +1,231 @@
+"""SoundStream VQ-VAE -- host-side mirror of the reference ``models/vq_brain.py``.
+
+Same class names, constructor kwargs, ``forward`` signatures, return conventions and state-dict
+keys as the reference (models/vq_brain.py:22-243), so this module drops into
+``notebooks_trainer/vq_brain_trainer.ipynb`` and ``utils/train_utils.py:138``.  What changes
+underneath:
+
+* the quantiser is ``frankenstein_b200.vector_quantize.VectorQuantize`` (tcgen05 search + fused
+  epilogue kernels) instead of the third-party ``vector_quantize_pytorch`` module;
+* ``custom_l1_loss`` is one fused masked-sum kernel (no ``nonzero`` host sync, no dynamic shape);
+* ``calculate_perp`` is computed from the code histogram (no ``[N, K]`` one-hot).
+
+The causal conv / transposed-conv stacks are cuDNN library convolutions exactly as in the
+reference (SURVEY.md section 8f row N1 lists them as the next kernel to write).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ._lib import DTYPE_CODE, FkError, check, lib, ptr, require_cuda, require_device, stream
+from .vector_quantize import VectorQuantize, _counter
+
+
+class CausalConv1d(nn.Conv1d):
+    """models/vq_brain.py:22-28 -- left padding of dilation * (k - 1)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.causal_padding = self.dilation[0] * (self.kernel_size[0] - 1)
+
+    def forward(self, x):
+        return self._conv_forward(F.pad(x, [self.causal_padding, 0]), self.weight, self.bias)
+
+
+class CausalConvTranspose1d(nn.ConvTranspose1d):
+    """models/vq_brain.py:31-45 -- transposed conv with the trailing k - s samples trimmed."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.causal_padding = (self.dilation[0] * (self.kernel_size[0] - 1) + self.output_padding[0] + 1
+                               - self.stride[0])
+
+    def forward(self, x, output_size=None):
+        if self.padding_mode != 'zeros':
+            raise ValueError('Only `zeros` padding mode is supported for ConvTranspose1d')
+        output_padding = self._output_padding(x, output_size, self.stride, self.padding, self.kernel_size,
+                                              self.dilation)
+        y = F.conv_transpose1d(x, self.weight, self.bias, self.stride, self.padding, output_padding, self.groups,
+                               self.dilation)
+        return y[..., :-self.causal_padding]
+
+
+def _interleave_elu(mods):
+    """[m0, ELU, m1, ELU, ..., mN] -- the Sequential indexing the reference checkpoints expect."""
+    out = []
+    for i, m in enumerate(mods):
+        if i:
+            out.append(nn.ELU())
+        out.append(m)
+    return nn.Sequential(*out)
+
+
+class ResidualUnit(nn.Module):
+    """x + Conv1x1(ELU(CausalConv3(x)))  (models/vq_brain.py:48-63)."""
+
+    def __init__(self, in_channels, out_channels, dilation):
+        super().__init__()
+        self.dilation = dilation
+        self.layers = _interleave_elu([
+            CausalConv1d(in_channels, out_channels, kernel_size=3, dilation=dilation),
+            nn.Conv1d(out_channels, in_channels, kernel_size=1),
+        ])
+
+    def forward(self, x):
+        return x + self.layers(x)
+
+
+def _residual_stack(ch, n=3):
+    return [ResidualUnit(ch, ch, dilation=1) for _ in range(n)]
+
+
+class EncoderBlock(nn.Module):
+    """3 residual units then a strided causal conv (k = 2*stride)  (models/vq_brain.py:66-90)."""
+
+    def __init__(self, in_channels, out_channels, stride):
+        super().__init__()
+        self.layers = _interleave_elu(_residual_stack(in_channels) + [
+            CausalConv1d(in_channels, out_channels, kernel_size=2 * stride, stride=stride)])
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+class DecoderBlock(nn.Module):
+    """strided causal transposed conv then 3 residual units  (models/vq_brain.py:93-117)."""
+
+    def __init__(self, in_channels, out_channels, stride):
+        super().__init__()
+        self.layers = _interleave_elu([
+            CausalConvTranspose1d(in_channels, out_channels, kernel_size=2 * stride, stride=stride)]
+            + _residual_stack(out_channels))
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+class _ChannelsFirstStack(nn.Module):
+    """[B, T, C] in and out; the conv stack itself runs channels-first like the reference."""
+
+    def forward(self, x):
+        return self.layers(x.transpose(1, 2)).transpose(1, 2)
+
+
+class Encoder(_ChannelsFirstStack):
+    """models/vq_brain.py:120-138: conv k5 -> 2 x EncoderBlock(stride 2) -> conv k3; T/4 tokens of width D."""
+
+    def __init__(self, C, D, n_electrodes):
+        super().__init__()
+        self.layers = _interleave_elu([
+            CausalConv1d(n_electrodes, C, kernel_size=5),
+            EncoderBlock(C, C, stride=2),
+            EncoderBlock(C, C, stride=2),
+            CausalConv1d(C, D, kernel_size=3),
+        ])
+
+
+class Decoder(_ChannelsFirstStack):
+    """models/vq_brain.py:141-159: mirror of the encoder."""
+
+    def __init__(self, C, D, n_channels_out):
+        super().__init__()
+        self.layers = _interleave_elu([
+            CausalConv1d(D, C, kernel_size=3),
+            DecoderBlock(C, C, stride=2),
+            DecoderBlock(C, C, stride=2),
+            CausalConv1d(C, n_channels_out, kernel_size=5),
+        ])
+
+
+class _MaskedL1(torch.autograd.Function):
+    """custom_l1_loss (models/vq_brain.py:220-227) as one fused forward and one fused backward kernel."""
+
+    @staticmethod
+    def forward(ctx, pred, gt):
+        require_cuda(pred, gt)
+        require_device()
+        ctx.pred_dtype = pred.dtype
+        if pred.dtype not in (torch.float32, torch.bfloat16):
+            pred = pred.float()
+        B, T, C = pred.shape
+        p = pred.contiguous()
+        g = gt.contiguous().float()
+        R = B * T
+        nb = lib().fk_masked_l1_partials(R)
+        dev = pred.device
+        row_valid = torch.empty(R, device=dev, dtype=torch.uint8)
+        ps = torch.empty(nb, device=dev, dtype=torch.float32)
+        pc = torch.empty(nb, device=dev, dtype=torch.float32)
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        denom = torch.empty(1, device=dev, dtype=torch.float32)
+        check(lib().fk_masked_l1_forward(ptr(p), DTYPE_CODE[p.dtype], ptr(g), R, C, ptr(row_valid), ptr(ps), ptr(pc),
+                                         ptr(_counter(dev)[1:]), ptr(loss), ptr(denom), stream()), "fk_masked_l1_forward")
+        ctx.save_for_backward(p, g, row_valid, denom)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        p, g, row_valid, denom = ctx.saved_tensors
+        B, T, C = p.shape
+        grad = torch.empty_like(p)
+        gl = g_loss.reshape(1).contiguous().float()
+        check(lib().fk_masked_l1_backward(ptr(p), DTYPE_CODE[p.dtype], ptr(g), ptr(row_valid), ptr(gl), ptr(denom), B * T,
+                                          C, ptr(grad), stream()), "fk_masked_l1_backward")
+        return grad.to(ctx.pred_dtype), None
+
+
+def perplexity(indices: torch.Tensor, codebook_size: int) -> torch.Tensor:
+    """calculate_perp (models/vq_brain.py:238-243) from the code histogram."""
+    require_cuda(indices)
+    require_device()
+    ind = indices.reshape(-1).contiguous()
+    bins = torch.empty(codebook_size, device=ind.device, dtype=torch.float32)
+    out = torch.empty(1, device=ind.device, dtype=torch.float32)
+    check(lib().fk_vq_perplexity(ptr(ind), ind.numel(), codebook_size, ptr(bins), ptr(out), stream()), "fk_vq_perplexity")
+    return out.view(())
+
+
+class SoundStream(nn.Module):
+    """models/vq_brain.py:162-243.  forward(x[B,T,n_electrodes]) -> (rec_loss + commit_loss [1], o [B,T,n_electrodes])."""
+
+    def __init__(self, C, D, codebook_size, n_electrodes, use_cosine_sim=True):
+        super().__init__()
+        self.codebook_size = codebook_size
+        self.encoder = Encoder(C=C, D=D, n_electrodes=n_electrodes)
+        self.quantizer = VectorQuantize(
+            dim=D,
+            codebook_size=codebook_size,
+            commitment_weight=0.25,
+            channel_last=True,
+            kmeans_init=True,
+            threshold_ema_dead_code=2,
+            use_cosine_sim=use_cosine_sim,
+        )
+        self.decoder = Decoder(C=C, D=D, n_channels_out=n_electrodes)
+        self.compute_perplexity = False     # the reference computes it and discards the value (vq_brain.py:212)
+        self.last_perplexity = None
+
+    def forward(self, x, targets=None, date_info=None):
+        e = self.encoder(x)
+        quantized, indices, commit_loss = self.quantizer(e)
+        if quantized.dtype != e.dtype and not torch.is_autocast_enabled():
+            quantized = quantized.to(e.dtype)      # module cast to bf16/fp16 without autocast
+        o = self.decoder(quantized)
+        if self.compute_perplexity:
+            self.last_perplexity = self.calculate_perp(indices)
+        rec_loss = self.custom_l1_loss(o, x)
+        total_loss = rec_loss + commit_loss
+        return total_loss, o
+
+    def custom_l1_loss(self, pred, gt):
+        return _MaskedL1.apply(pred, gt)
+
+    def get_quantize_vectors(self, x):
+        e = self.encoder(x)
+        quantized, indices, commit_loss = self.quantizer(e)
+        return indices, quantized
+
+    def calculate_perp(self, indices):
+        return perplexity(indices, self.codebook_size)

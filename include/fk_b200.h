@@ -1,0 +1,102 @@
+/* frankenstein-b200 C ABI  (libfk_b200.so, compiled for sm_100a only)
+ *
+ * Conventions:
+ *  - plain pointers and sizes, no torch types; all pointers are DEVICE pointers unless stated;
+ *  - the caller owns every buffer (kernels never allocate or free);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no implicit sync;
+ *  - return value: 0 = ok, negative = error (fk_last_error() has the text);
+ *    -1 bad argument, -2 CUDA launch error, -3 unsupported shape, -4 driver entry point missing;
+ *  - no CPU path exists: without a Blackwell GPU every compute entry point fails.
+ *
+ * Each entry point names the reference interface it replaces.  "VQ" is the third-party
+ * vector_quantize_pytorch.VectorQuantize constructed at models/vq_brain.py:184-193 and called at
+ * models/vq_brain.py:209 / :233 (restated in oracle/vector_quantize_ref.py).
+ */
+#ifndef FK_B200_H
+#define FK_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- bookkeeping ---------------------------------------------------------------------------- */
+const char* fk_last_error(void);
+long long fk_launch_count(void);       /* kernels/memsets enqueued by this library since reset */
+void fk_reset_launch_count(void);
+int fk_abi_version(void);
+int fk_target_sm(void);                 /* 100 */
+int fk_device_ok(void);                 /* 1 if the current device is compute capability 10.x */
+
+/* ---- VQ: operand preparation ---------------------------------------------------------------- */
+/* VectorQuantize.forward `x = x.float()` + CosineSimCodebook `l2norm(x)` (F.normalize, eps 1e-12).
+ * e: [N, D] dtype 0=f32 1=bf16 2=f16.  xn (nullable): fp32 [N, D] transformed rows;
+ * x_bf16: [N, Dp] zero-padded tensor-core operand; inv_norm: [N] (cosine only). */
+int fk_vq_prepare_input(const void* e, int dtype, long long N, int D, int Dp, int use_cosine, float* xn,
+                        void* x_bf16, float* inv_norm, void* stream);
+/* Codebook operand for the search: cb_bf16 [K, Dp], c2pad [Kpad] = |c|^2 (0 for cosine), +inf pad. */
+int fk_vq_prepare_codebook(const float* embed, int K, int D, int Dp, int Kpad, int use_cosine, void* cb_bf16,
+                           float* c2pad, void* stream);
+
+/* ---- VQ: nearest-codeword search (tcgen05 / TMEM / TMA) -------------------------------------- */
+/* Replaces `dist = -cdist(x, embed)` / `einsum('h n d, h c d -> h n c')` + `argmax` in
+ * Euclidean/CosineSimCodebook.forward.  Writes per row S slots of (top-2 value, top-2 index);
+ * S = fk_vq_search_slots(N, K, max_ctas) (host helper, no GPU work).  max_ctas <= 0: all SMs. */
+int fk_vq_search_slots(long long N, int K, int max_ctas);
+int fk_vq_search(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                 int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, void* stream);
+
+/* Same kernel; additionally dumps the raw fp32 accumulators x.c to dbg_scores [N, roundup(K,128)] (tests). */
+int fk_vq_search_debug(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                       int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, float* dbg_scores,
+                       void* stream);
+
+/* ---- VQ: exact re-score + gather + straight-through + commitment loss ------------------------ */
+/* Replaces gumbel_sample(argmax), `quantize = onehot @ embed`, `x + (quantize - x).detach()` and
+ * `F.mse_loss(quantize.detach(), x) * commitment_weight` (VectorQuantize.forward).
+ * indices: int64 [N]; quantize: fp32 [N, D] (nullable when !training: indices only); loss: [1]; partials: [fk_vq_finish_partials(N)];
+ * counter: one zero-initialised uint32 that the kernel leaves at zero. */
+long long fk_vq_finish_partials(long long N);
+int fk_vq_finish(const float* xn, const float* embed, const float* cand_val, const int* cand_idx, long long N,
+                 int K, int D, int S, int use_cosine, int training, float commitment_weight, long long* indices,
+                 float* quantize, float* loss, float* partials, unsigned int* counter, void* stream);
+
+/* ---- VQ: EMA statistics, EMA finalize + dead-code reset -------------------------------------- */
+/* Replaces `bins = onehot.sum()` and `embed_sum = einsum('h n d, h n c -> h c d')`.
+ * stats: fp32 [K*D + K] = embed_sum || bins, one packed buffer so data-parallel ranks need ONE
+ * all-reduce (zeroed inside the call). */
+int fk_vq_ema_stats(const float* xn, const long long* indices, long long N, int K, int D, float* stats,
+                    void* stream);
+/* Replaces ema_inplace x2, laplace_smoothing, `embed.copy_`, (cosine) l2norm and expire_codes_/
+ * replace; also writes the next search's operand.  sample_rows (nullable): int64 [n_sample] rows of
+ * xn; the i-th expired code (ascending code index) takes row sample_rows[i % n_sample].
+ * Workspaces: total_ws [1] float, expire_rank_ws [K] int, n_expired [1] int (output). */
+int fk_vq_ema_update(const float* stats, float* cluster_size, float* embed_avg, float* embed, int K, int D, int Dp,
+                     int Kpad, int use_cosine, float decay, float eps, float threshold,
+                     const long long* sample_rows, int n_sample, const float* xn, long long N, void* cb_bf16,
+                     float* c2pad, float* total_ws, int* expire_rank_ws, int* n_expired, void* stream);
+
+/* ---- VQ: backward ---------------------------------------------------------------------------- */
+/* autograd of VectorQuantize.forward w.r.t. its input: g_out (nullable) [N, D], g_loss (nullable) [1]. */
+int fk_vq_backward(const float* g_out, const float* g_loss, const float* xn, const float* quantize,
+                   const float* inv_norm, long long N, int D, int use_cosine, float commitment_weight,
+                   float* grad_in, void* stream);
+
+/* ---- VQ: k-means init (upstream `kmeans`), one mean update from packed stats ----------------- */
+int fk_vq_kmeans_update(const float* stats, float* means, int K, int D, int Dp, int Kpad, int use_cosine,
+                        void* cb_bf16, float* c2pad, void* stream);
+
+/* ---- SoundStream.calculate_perp (models/vq_brain.py:238-243) --------------------------------- */
+int fk_vq_perplexity(const long long* indices, long long N, int K, float* bins_ws, float* out, void* stream);
+
+/* ---- SoundStream.custom_l1_loss (models/vq_brain.py:220-227) --------------------------------- */
+long long fk_masked_l1_partials(long long R);
+int fk_masked_l1_forward(const void* pred, int dtype, const float* gt, long long R, int C, unsigned char* row_valid,
+                         float* part_sum, float* part_cnt, unsigned int* counter, float* loss, float* denom,
+                         void* stream);
+int fk_masked_l1_backward(const void* pred, int dtype, const float* gt, const unsigned char* row_valid,
+                          const float* g_loss, const float* denom, long long R, int C, void* grad_pred, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FK_B200_H */
