@@ -71,17 +71,23 @@ vq_prepare_codebook_kernel(const float* __restrict__ embed, int K, int D, int Dp
 }
 
 // ------------------------------------------------------------------------------------------
-// K2-K4: merge the candidate slots of a row to the approximate top-2, re-score both in exact
-// fp32 with the reference's formula, pick with lowest-index tie-break, gather the fp32 codeword,
-// straight-through output, commitment-loss partial sums.
+// K2-K4: merge the candidate slots of a row, take the (up to) 4 best approximate keys, re-score in
+// exact fp32 every candidate that lies within the bf16 error margin of the best key, pick with the
+// reference's formula and lowest-index tie-break, gather the fp32 codeword, straight-through
+// output, commitment-loss partial sums.
 //   Euclidean (upstream cdist): d = sqrt(max(|x|^2 + |c|^2 - 2 x.c, 0)), minimise
 //   cosine                    : s = x.c, maximise
+// Margin: the bf16 rounding of both operands perturbs x.c by a zero-mean error of standard
+// deviation ~ 0.8 * 2^-9 * sqrt(sum x_d^2 c_d^2) <= 0.8 * 2^-9 * |x||c|; the key carries alpha
+// (<= 2) times that.  margin = |x||c| * 2^-9 * 32 / sqrt(D) is > 12 sigma for non-sparse vectors.
 // ------------------------------------------------------------------------------------------
+constexpr int kFinishCand = 4;   // must match kCand of the search kernel
+
 struct FinishParams {
   const float* xn;       // [N, D]
   const float* embed;    // [K, D]
-  const float* cand_val; // [N, S, 2]
-  const int* cand_idx;   // [N, S, 2]
+  const float* cand_val; // [N, S, 4]
+  const int* cand_idx;   // [N, S, 4]
   long long* indices;    // [N]
   float* quantize;       // [N, D]
   float* partials;       // [gridDim.x]
@@ -90,7 +96,12 @@ struct FinishParams {
   long long N;
   int K, D, S, cosine, training;
   float loss_scale;      // commitment_weight / (N * D)
+  float margin_scale;    // 2^-9 * 32 / sqrt(D)
 };
+
+__device__ __forceinline__ bool pair_less(float va, int ia, float vb, int ib) {
+  return (va < vb) || (va == vb && ia < ib);
+}
 
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 vq_finish_kernel(const FinishParams p) {
@@ -98,51 +109,74 @@ vq_finish_kernel(const FinishParams p) {
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5);
+  const float inf = __int_as_float(0x7f800000);
   float sq_err = 0.f;
   if (row < p.N) {
-    // ---- approximate top-2 over the slots (every lane computes the same thing) ----
-    float b1 = __int_as_float(0x7f800000), b2 = b1;
-    int i1 = -1, i2 = -1;
-    for (int s = 0; s < p.S * 2; ++s) {
-      const int j = p.cand_idx[row * p.S * 2 + s];
-      const float v = p.cand_val[row * p.S * 2 + s];
-      if (j < 0 || j >= p.K) continue;
-      // order by (value, index): slots come from disjoint code ranges in ascending order, but be explicit
-      const bool lt1 = (v < b1) || (v == b1 && j < i1) || i1 < 0;
-      const bool lt2 = (v < b2) || (v == b2 && j < i2) || i2 < 0;
-      if (lt1) { b2 = b1; i2 = i1; b1 = v; i1 = j; }
-      else if (lt2) { b2 = v; i2 = j; }
+    // ---- the 4 smallest (key, index) pairs over all slots, one warp-wide selection round each ----
+    const int C = p.S * kFinishCand;
+    const float* cv = p.cand_val + row * C;
+    const int* ci = p.cand_idx + row * C;
+    float sel_v[kFinishCand];
+    int sel_i[kFinishCand];
+    float prev_v = -inf;
+    int prev_i = -1;
+#pragma unroll
+    for (int r = 0; r < kFinishCand; ++r) {
+      float bv = inf;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) {
+        const int j = ci[c];
+        const float v = cv[c];
+        if (j < 0 || j >= p.K || !(v < inf)) continue;
+        if (r > 0 && !pair_less(prev_v, prev_i, v, j)) continue;     // already selected
+        if (pair_less(v, j, bv, bi)) { bv = v; bi = j; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (pair_less(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      sel_v[r] = bv;
+      sel_i[r] = (bi == 0x7fffffff) ? -1 : bi;
+      prev_v = bv;
+      prev_i = bi;
     }
-    if (i1 < 0) i1 = 0;          // all-NaN row: no candidate survived a comparison
+    if (sel_i[0] < 0) sel_i[0] = 0;          // all-NaN row: nothing survived a comparison
     // ---- exact fp32 scores ----
     const float* xr = p.xn + row * p.D;
-    const float* c1 = p.embed + static_cast<long long>(i1) * p.D;
-    const float* c2 = p.embed + static_cast<long long>(i2 < 0 ? i1 : i2) * p.D;
-    float xx = 0.f, d1 = 0.f, d2 = 0.f, n1 = 0.f, n2 = 0.f;
+    float xx = 0.f;
     for (int d = lane * 4; d < p.D; d += 128) {
       const float4 x = *reinterpret_cast<const float4*>(xr + d);
-      const float4 a = *reinterpret_cast<const float4*>(c1 + d);
-      const float4 b = *reinterpret_cast<const float4*>(c2 + d);
       xx += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
-      d1 += x.x * a.x + x.y * a.y + x.z * a.z + x.w * a.w;
-      d2 += x.x * b.x + x.y * b.y + x.z * b.z + x.w * b.w;
-      n1 += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-      n2 += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
     }
-    xx = warp_sum(xx); d1 = warp_sum(d1); d2 = warp_sum(d2); n1 = warp_sum(n1); n2 = warp_sum(n2);
-    int best = i1;
-    if (i2 >= 0) {
-      bool second_wins;
-      if (p.cosine) {
-        second_wins = (d2 > d1) || (d2 == d1 && i2 < i1);
-      } else {
-        const float e1 = sqrtf(fmaxf(xx + n1 - 2.f * d1, 0.f));
-        const float e2 = sqrtf(fmaxf(xx + n2 - 2.f * d2, 0.f));
-        second_wins = (e2 < e1) || (e2 == e1 && i2 < i1);
+    xx = warp_sum(xx);
+    int best = sel_i[0];
+    float best_score = 0.f, margin = 0.f;
+#pragma unroll
+    for (int r = 0; r < kFinishCand; ++r) {
+      if (r > 0 && (sel_i[r] < 0 || !(sel_v[r] <= sel_v[0] + margin))) break;   // warp-uniform
+      const float* c = p.embed + static_cast<long long>(sel_i[r]) * p.D;
+      float dot = 0.f, nn = 0.f;
+      for (int d = lane * 4; d < p.D; d += 128) {
+        const float4 x = *reinterpret_cast<const float4*>(xr + d);
+        const float4 a = *reinterpret_cast<const float4*>(c + d);
+        dot += x.x * a.x + x.y * a.y + x.z * a.z + x.w * a.w;
+        nn += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
       }
-      if (second_wins) best = i2;
+      dot = warp_sum(dot);
+      nn = warp_sum(nn);
+      // smaller-is-better exact score in the reference's own arithmetic
+      const float score = p.cosine ? -dot : sqrtf(fmaxf(xx + nn - 2.f * dot, 0.f));
+      if (r == 0) {
+        best_score = score;
+        margin = sqrtf(xx * nn) * p.margin_scale + fabsf(sel_v[0]) * (1.f / 2048.f);
+      } else if (score < best_score || (score == best_score && sel_i[r] < best)) {
+        best_score = score;
+        best = sel_i[r];
+      }
     }
-    const float* cq = (best == i1) ? c1 : c2;
+    const float* cq = p.embed + static_cast<long long>(best) * p.D;
     if (lane == 0) p.indices[row] = best;
     float* qr = p.quantize + row * p.D;
     for (int d = lane * 4; d < p.D && p.quantize != nullptr; d += 128) {
@@ -481,6 +515,7 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_finish(const float* 
   p.indices = indices; p.quantize = quantize; p.partials = partials; p.counter = counter; p.loss = loss;
   p.N = N; p.K = K; p.D = D; p.S = S; p.cosine = use_cosine; p.training = training;
   p.loss_scale = static_cast<float>(static_cast<double>(commitment_weight) / (static_cast<double>(N) * D));
+  p.margin_scale = 32.f / 512.f / sqrtf(static_cast<float>(D));
   vq_finish_kernel<<<row_blocks(N), kRowsPerBlock * 32, 0, stream>>>(p);
   FK_CHECK_LAUNCH();
   fk_count_launch();

@@ -10,17 +10,20 @@
 //   Euclidean: alpha = -2, c2[k] = |c_k|^2   (|x|^2 is row-constant, sqrt/clamp are monotone)
 //   cosine   : alpha = -1, c2[k] = 0         (argmax of the similarity)
 // c2 is padded to a multiple of BN with +inf so that out-of-range codes can never win.
-// Because bf16 operands perturb near-ties, the kernel keeps the TOP-2 (value, index) per row per
-// work segment; fk_vq_finish re-scores those candidates in exact fp32 and applies the reference's
-// tie rule (lowest index wins).
+// Because bf16 operands perturb near-ties, the kernel does not commit to one index: every epilogue
+// thread keeps a running minimum per column class (32 classes = column mod 32, 3 instructions per
+// element, no branches) with the tile id packed into the low mantissa bits of the key, and writes
+// its 4 best classes per work segment.  fk_vq_finish merges the candidates of a row, re-scores the
+// ones inside the bf16 error margin in exact fp32 and applies the reference's tie rule (lowest
+// index wins).
 //
 // Tiling: CTA tile = 256 rows (two M=128 accumulators) x 128 codes, K-depth = D (<= 256, whole
 // depth resident for X).  A work unit is one (row block, code tile) pair; the W = RB*T units are
 // cut into gridDim.x contiguous ranges (persistent CTAs, perfect balance to within one unit), so a
 // CTA covers at most a few row blocks ("segments") and writes one candidate slot per segment.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 =
-// TMEM allocator, warps 4-7 / 8-11 = epilogue for accumulator rows 0-127 / 128-255.
+// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 =
+// TMEM allocator, warps 4-19 = epilogue (TMEM lane quarter x accumulator half x column half).
 #include "common.cuh"
 
 namespace fk {
@@ -30,70 +33,62 @@ constexpr int kBN = 128;          // codes per tile (UMMA_N)
 constexpr int kSlabK = 64;        // bf16 elements per 128-byte swizzled row
 constexpr int kXSlabBytes = kBM * 128;   // 32 KB
 constexpr int kBSlabBytes = kBN * 128;   // 16 KB
-constexpr int kSearchThreads = 384;
+constexpr int kSearchThreads = 640;       // 4 control warps + 16 epilogue warps
+constexpr int kEpilogueThreads = 512;
 constexpr int kMaxStages = 8;
 
 struct SearchParams {
   const float* c2pad;   // [T * kBN]
-  float* cand_val;      // [N][S][2]
-  int* cand_idx;        // [N][S][2]
+  float* cand_val;      // [N][S][kCand] keys (approximate scores)
+  int* cand_idx;        // [N][S][kCand] code indices, -1 = none
+  uint32_t tag_mask;    // low mantissa bits that carry the tile tag
   float* dbg_scores;    // optional [N][T*kBN] raw accumulators (tests only)
   long long N;
   int K, nslab, T, RB, S, nstage;
   float alpha;
 };
 
-__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&r)[16]) {
   // tcgen05.wait::ld with the destination registers as in/out operands, so that no use of r[] can
   // be scheduled above the wait.
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
-                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
-                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
-                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 "+r"(r[15])
                :: "memory");
 }
 
-struct Top2 {
-  float b1, b2;
-  int i1, i2;
-  __device__ __forceinline__ void update(float v, int j) {
-    const bool p1 = v < b1, p2 = v < b2;
-    i2 = p1 ? i1 : (p2 ? j : i2);
-    b2 = p1 ? b1 : (p2 ? v : b2);
-    i1 = p1 ? j : i1;
-    b1 = p1 ? v : b1;
-  }
-};
+constexpr int kCand = 4;          // candidates written per (row, slot)
 
-// 32 accumulator columns of this thread's row: chunk-of-8 minimum first (2 instr / element), the
-// index-tracking update only for chunks that can change the running top-2.
-__device__ __forceinline__ void scan32(const uint32_t (&r)[32], const float* c2s, float alpha, int jbase, Top2& t) {
+// 16 accumulator columns of this thread's row -> running class minima.  key = score with the low
+// `tag` bits of the mantissa replaced by the tile tag (relative precision loss <= 2^-13, far below
+// the bf16 operand noise); +inf padding columns turn into NaN keys, which fminf ignores.
+__device__ __forceinline__ void scan16(const uint32_t (&r)[16], const float* c2s, float alpha, uint32_t keep_mask,
+                                       uint32_t tag, float (&m)[32], int class_off, float* dbg) {
+  if (dbg != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dbg[i] = __uint_as_float(r[i]);
+  }
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float4 ca = *reinterpret_cast<const float4*>(c2s + g * 8);
-    const float4 cb = *reinterpret_cast<const float4*>(c2s + g * 8 + 4);
-    float v[8];
-    v[0] = fmaf(__uint_as_float(r[g * 8 + 0]), alpha, ca.x);
-    v[1] = fmaf(__uint_as_float(r[g * 8 + 1]), alpha, ca.y);
-    v[2] = fmaf(__uint_as_float(r[g * 8 + 2]), alpha, ca.z);
-    v[3] = fmaf(__uint_as_float(r[g * 8 + 3]), alpha, ca.w);
-    v[4] = fmaf(__uint_as_float(r[g * 8 + 4]), alpha, cb.x);
-    v[5] = fmaf(__uint_as_float(r[g * 8 + 5]), alpha, cb.y);
-    v[6] = fmaf(__uint_as_float(r[g * 8 + 6]), alpha, cb.z);
-    v[7] = fmaf(__uint_as_float(r[g * 8 + 7]), alpha, cb.w);
-    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
-    if (m < t.b2) {
+    const float4 c = *reinterpret_cast<const float4*>(c2s + g * 4);
+    const float cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) t.update(v[e], jbase + g * 8 + e);
+    for (int e = 0; e < 4; ++e) {
+      const float v = fmaf(__uint_as_float(r[g * 4 + e]), alpha, cc[e]);
+      const float key = __uint_as_float((__float_as_uint(v) & keep_mask) | tag);
+      m[class_off + g * 4 + e] = fminf(m[class_off + g * 4 + e], key);
     }
   }
-}
-
-__device__ __noinline__ void dump32(const uint32_t (&r)[32], float* dst) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(r[i]);
 }
 
 __global__ void __launch_bounds__(kSearchThreads, 1)
@@ -130,7 +125,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     mbar_init(x_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], 16);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -211,61 +206,90 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    const int h = (warp - 4) >> 2;          // accumulator half == warpgroup
-    const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int tid128 = (warp - 4 - h * 4) * 32 + lane;
-    float* my_c2 = c2s + h * kBN;
+    // 16 warps: q = TMEM lane quarter (fixed by warp id % 4), h = accumulator half (rows 0-127 / 128-255),
+    // cpart = which 64 of the tile's 128 columns this warp scans.  Every (row, cpart) keeps its own
+    // top-2 and writes its own candidate slot, so no cross-warp merge is needed here.
+    const int e = warp - 4;
+    const int q = e & 3, h = (e >> 2) & 1, cpart = e >> 3;
+    const int etid = threadIdx.x - 128;                  // 0..511
+    const float inf = __int_as_float(0x7f800000);
+    float m[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m[i] = inf;
+    const uint32_t keep_mask = ~p.tag_mask;
+    // c2 of the first tile; later tiles are prefetched one tile ahead into the other buffer
+    if (etid < kBN && u_begin < u_end) c2s[etid] = __ldg(p.c2pad + (u_begin % p.T) * kBN + etid);
+    named_bar_sync(1, kEpilogueThreads);
     uint32_t tc = 0;
-    for (long long u = u_begin; u < u_end;) {
-      const int rb = static_cast<int>(u / p.T), t0 = static_cast<int>(u % p.T);
-      const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
-      Top2 best;
-      best.b1 = best.b2 = __int_as_float(0x7f800000);
-      best.i1 = best.i2 = -1;
-      for (int t = t0; t < t0 + nt; ++t, ++tc) {
-        const uint32_t as = tc & 1;
-        named_bar_sync(1 + h, 128);                       // previous tile's c2 reads are done
-        my_c2[tid128] = __ldg(p.c2pad + static_cast<long long>(t) * kBN + tid128);
-        named_bar_sync(1 + h, 128);
-        mbar_wait(&tmem_full[as], (tc >> 1) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (h * 2 + as) * kBN;
-        uint32_t ra[32], rb2[32];
-        const long long drow = static_cast<long long>(rb) * kBM + h * 128 + q * 32 + lane;
-        float* dbg = (p.dbg_scores != nullptr && drow < p.N)
-                         ? p.dbg_scores + drow * (static_cast<long long>(p.T) * kBN) + static_cast<long long>(t) * kBN
-                         : nullptr;
-        tmem_ld32(taddr, ra);
-        tmem_wait_ld_dep(ra);
-        tmem_ld32(taddr + 32, rb2);
-        if (dbg) dump32(ra, dbg);
-        scan32(ra, my_c2, p.alpha, t * kBN, best);
-        tmem_wait_ld_dep(rb2);
-        tmem_ld32(taddr + 64, ra);
-        if (dbg) dump32(rb2, dbg + 32);
-        scan32(rb2, my_c2 + 32, p.alpha, t * kBN + 32, best);
-        tmem_wait_ld_dep(ra);
-        tmem_ld32(taddr + 96, rb2);
-        if (dbg) dump32(ra, dbg + 64);
-        scan32(ra, my_c2 + 64, p.alpha, t * kBN + 64, best);
-        tmem_wait_ld_dep(rb2);
-        if (dbg) dump32(rb2, dbg + 96);
-        scan32(rb2, my_c2 + 96, p.alpha, t * kBN + 96, best);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      }
-      // candidate slot of this segment inside its row block
-      const long long ufirst = static_cast<long long>(rb) * p.T;
-      const int first_cta = static_cast<int>(((ufirst + 1) * G - 1) / W);
-      const int slot = static_cast<int>(blockIdx.x) - first_cta;
+    int t_seg0 = static_cast<int>(u_begin % p.T);        // first tile of the current segment
+    for (long long u = u_begin; u < u_end; ++u, ++tc) {
+      const int rb = static_cast<int>(u / p.T), t = static_cast<int>(u % p.T);
+      const uint32_t as = tc & 1;
+      float c2_next = 0.f;
+      const bool have_next = (u + 1 < u_end) && etid < kBN;
+      if (have_next) c2_next = __ldg(p.c2pad + ((u + 1) % p.T) * kBN + etid);
+      const float* my_c2 = c2s + as * kBN + cpart * 64;
+      const uint32_t tag = static_cast<uint32_t>(t - t_seg0) * 2u;
+      mbar_wait(&tmem_full[as], (tc >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (h * 2 + as) * kBN + cpart * 64;
       const long long row = static_cast<long long>(rb) * kBM + h * 128 + q * 32 + lane;
-      if (row < p.N && slot >= 0 && slot < p.S) {
-        const long long o = (row * p.S + slot) * 2;
-        *reinterpret_cast<float2*>(p.cand_val + o) = make_float2(best.b1, best.b2);
-        *reinterpret_cast<int2*>(p.cand_idx + o) = make_int2(best.i1, best.i2);
+      float* dbg = (p.dbg_scores != nullptr && row < p.N)
+                       ? p.dbg_scores + row * (static_cast<long long>(p.T) * kBN) + static_cast<long long>(t) * kBN + cpart * 64
+                       : nullptr;
+      uint32_t ra[16], rb2[16];
+      tmem_ld16(taddr, ra);
+      tmem_wait_ld_dep(ra);
+      tmem_ld16(taddr + 16, rb2);
+      scan16(ra, my_c2, p.alpha, keep_mask, tag, m, 0, dbg);
+      tmem_wait_ld_dep(rb2);
+      tmem_ld16(taddr + 32, ra);
+      scan16(rb2, my_c2 + 16, p.alpha, keep_mask, tag, m, 16, dbg ? dbg + 16 : nullptr);
+      tmem_wait_ld_dep(ra);
+      tmem_ld16(taddr + 48, rb2);
+      scan16(ra, my_c2 + 32, p.alpha, keep_mask, tag + 1u, m, 0, dbg ? dbg + 32 : nullptr);
+      tmem_wait_ld_dep(rb2);
+      // all TMEM reads of this accumulator stage are done: hand it back before the last scan
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      scan16(rb2, my_c2 + 48, p.alpha, keep_mask, tag + 1u, m, 16, dbg ? dbg + 48 : nullptr);
+      if (have_next) c2s[(as ^ 1) * kBN + etid] = c2_next;
+      named_bar_sync(1, kEpilogueThreads);      // c2 of the next tile visible; this tile's c2 reads finished
+      if (t == p.T - 1 || u + 1 == u_end) {
+        // ---- end of a segment: the kCand smallest class keys of this (row, cpart) -> its candidate slot ----
+        float cv[kCand];
+        int ci[kCand];
+#pragma unroll
+        for (int r = 0; r < kCand; ++r) {
+          float mn = m[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mn = fminf(mn, m[i]);
+          int cls = -1;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool hit = (m[i] == mn) && (cls < 0);
+            cls = hit ? i : cls;
+            m[i] = hit ? inf : m[i];
+          }
+          const uint32_t tg = __float_as_uint(mn) & p.tag_mask;
+          // class -> column: classes 0-15 come from loads 0/2, 16-31 from loads 1/3; tag bit 0 = upper 32 columns
+          const int col = cpart * 64 + static_cast<int>(tg & 1u) * 32 + cls;
+          cv[r] = mn;
+          ci[r] = (mn < inf && cls >= 0) ? (t_seg0 + static_cast<int>(tg >> 1)) * kBN + col : -1;
+        }
+        const long long ufirst = static_cast<long long>(rb) * p.T;
+        const int first_cta = static_cast<int>(((ufirst + 1) * G - 1) / W);
+        const int slot = (static_cast<int>(blockIdx.x) - first_cta) * 2 + cpart;
+        if (row < p.N && slot >= 0 && slot < p.S) {
+          const long long o = (row * p.S + slot) * kCand;
+          *reinterpret_cast<float4*>(p.cand_val + o) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+          *reinterpret_cast<int4*>(p.cand_idx + o) = make_int4(ci[0], ci[1], ci[2], ci[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m[i] = inf;
+        t_seg0 = 0;                                   // the next segment starts a new row block at tile 0
       }
-      u += nt;
     }
   }
 
@@ -335,7 +359,7 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_search_slots(long lo
     const long long last = (((rb + 1) * T - 1 + 1) * G - 1) / W;
     if (last - first + 1 > S) S = static_cast<int>(last - first + 1);
   }
-  return S;
+  return 2 * S;   // two column halves per segment
 }
 
 extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
@@ -378,6 +402,12 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const v
   p.RB = static_cast<int>(RB);
   p.S = S;
   p.alpha = use_cosine ? -1.f : -2.f;
+  {
+    uint32_t need = static_cast<uint32_t>(2 * T), bits = 1;
+    while ((1u << bits) < need) ++bits;
+    FK_REQUIRE(bits <= 12, "fk_vq_search: codebook too large for the packed tile tag (K <= 262144)");
+    p.tag_mask = (1u << bits) - 1u;
+  }
   const int fixed = p.nslab * kXSlabBytes + 2 * kBN * 4 + 256 /*barriers*/;
   int nstage = (232448 - 1024 /*static*/ - fixed) / kBSlabBytes;
   if (nstage > kMaxStages) nstage = kMaxStages;
@@ -393,7 +423,7 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const v
     attr_set = true;
   }
   // unused slots must read as "no candidate"
-  if (cudaMemsetAsync(cand_idx, 0xFF, static_cast<size_t>(N) * S * 2 * sizeof(int), stream) != cudaSuccess) return FK_ERR_CUDA;
+  if (cudaMemsetAsync(cand_idx, 0xFF, static_cast<size_t>(N) * S * kCand * sizeof(int), stream) != cudaSuccess) return FK_ERR_CUDA;
   vq_search_kernel<<<static_cast<unsigned>(G), kSearchThreads, smem_bytes, stream>>>(tx, tcm, p);
   FK_CHECK_LAUNCH();
   fk_count_launch(2);

@@ -25,6 +25,7 @@ from . import _lib
 from ._lib import DTYPE_CODE, FkError, check, lib, ptr, require_cuda, require_device, stream
 
 BN = 128  # code tile of the search kernel (c2 padding granularity)
+CAND = 4  # candidates per (row, slot) written by the search kernel
 
 
 def _round_up(a: int, b: int) -> int:
@@ -67,7 +68,7 @@ def prepare_codebook(embed: torch.Tensor, use_cosine: bool, cb: Optional[torch.T
 
 
 def search(xb: torch.Tensor, cb: torch.Tensor, c2pad: torch.Tensor, K: int, use_cosine: bool, max_ctas: int = 0):
-    """tcgen05 search -> (cand_val [N,S,2] fp32, cand_idx [N,S,2] int32)."""
+    """tcgen05 search -> (cand_val [N,S,4] fp32 keys, cand_idx [N,S,4] int32 code indices, -1 = none)."""
     require_cuda(xb, cb, c2pad)
     require_device()
     N, Dp = xb.shape
@@ -76,8 +77,8 @@ def search(xb: torch.Tensor, cb: torch.Tensor, c2pad: torch.Tensor, K: int, use_
     if max_ctas <= 0:
         max_ctas = torch.cuda.get_device_properties(xb.device).multi_processor_count
     S = lib().fk_vq_search_slots(N, K, max_ctas)
-    cand_val = torch.empty(N, S, 2, device=xb.device, dtype=torch.float32)
-    cand_idx = torch.empty(N, S, 2, device=xb.device, dtype=torch.int32)
+    cand_val = torch.empty(N, S, CAND, device=xb.device, dtype=torch.float32)
+    cand_idx = torch.empty(N, S, CAND, device=xb.device, dtype=torch.int32)
     check(lib().fk_vq_search(ptr(xb), ptr(cb), ptr(c2pad), N, K, Dp, int(use_cosine), ptr(cand_val), ptr(cand_idx), S,
                              max_ctas, stream()), "fk_vq_search")
     return cand_val, cand_idx

@@ -39,7 +39,7 @@ int fk_vq_prepare_codebook(const float* embed, int K, int D, int Dp, int Kpad, i
 
 /* ---- VQ: nearest-codeword search (tcgen05 / TMEM / TMA) -------------------------------------- */
 /* Replaces `dist = -cdist(x, embed)` / `einsum('h n d, h c d -> h n c')` + `argmax` in
- * Euclidean/CosineSimCodebook.forward.  Writes per row S slots of (top-2 value, top-2 index);
+ * Euclidean/CosineSimCodebook.forward.  Writes per row S slots of 4 candidates (approximate key, code index; -1 = none): cand_val/cand_idx are [N, S, 4];
  * S = fk_vq_search_slots(N, K, max_ctas) (host helper, no GPU work).  max_ctas <= 0: all SMs. */
 int fk_vq_search_slots(long long N, int K, int max_ctas);
 int fk_vq_search(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,

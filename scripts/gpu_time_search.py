@@ -25,6 +25,9 @@ def time_fn(fn, iters=20, warm=5):
 
 def main():
     shapes = [(4096, 512, 64), (16384, 8192, 256), (16384, 512, 256), (16384, 2048, 256), (16384, 32768, 256), (16384, 65536, 256)]
+    if "--shape" in sys.argv:
+        i = sys.argv.index("--shape")
+        shapes = [tuple(int(v) for v in sys.argv[i + 1:i + 4])]
     out = []
     for N, K, D in shapes:
         X = torch.randn(N, D, device="cuda"); C = torch.randn(K, D, device="cuda")
