@@ -1,0 +1,317 @@
+// Bandwidth-bound fused kernels of the transformer blocks: LayerNorm / RMSNorm forward + backward and
+// the SwiGLU gate.  One warp per row, 16-byte accesses, fp32 statistics; roofline = HBM.
+//
+// Reference ops: nn.LayerNorm (models/brainformer.py:237-239,287; eps 1e-5, affine) which the
+// reference runs as ATen native_layer_norm; RMSNorm (models/simple_mae:181-192: fp32
+// x * rsqrt(mean(x^2) + 1e-6), cast back, times weight -- five eager launches in the reference);
+// MLP gate silu(w1 x) * (w3 x) (models/brainformer.py:123-124).
+#include "common.cuh"
+
+namespace fk {
+
+constexpr int kNormWarps = 8;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x), b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    v[0] = __bfloat162float(a.x); v[1] = __bfloat162float(a.y); v[2] = __bfloat162float(b.x); v[3] = __bfloat162float(b.y);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward: y = (x - mean) * rstd * w + b   (rms: y = x * rstd * w, rstd = rsqrt(mean(x^2) + eps))
+// MAXV = ceil(D / 128) float4 groups per lane (D <= 128 * MAXV)
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut, int MAXV>
+__global__ void __launch_bounds__(kNormWarps * 32)
+norm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, TOut* __restrict__ y,
+                float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int D, float eps, int rms) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kNormWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const TIn* xr = x + row * D;
+  float v[MAXV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int d = (i * 32 + lane) * 4;
+    if (d < D) { Vec4<TIn>::load(xr + d, v[i]); s += v[i][0] + v[i][1] + v[i][2] + v[i][3]; }
+    else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+  }
+  float mean = 0.f;
+  if (!rms) mean = warp_sum(s) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int d = (i * 32 + lane) * 4;
+    if (d < D) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float c = v[i][j] - mean; ss += c * c; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  TOut* yr = y + row * D;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int d = (i * 32 + lane) * 4;
+    if (d < D) {
+      float wv[4], bv[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+      Vec4<float>::load(w + d, wv);
+      if (bias) Vec4<float>::load(bias + d, bv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mean) * rstd * wv[j] + bv[j];
+      Vec4<TOut>::store(yr + d, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: dx = rstd * (gw - mean(gw) - xhat * mean(gw * xhat))   (rms: no mean(gw) term)
+// dw / db partial sums per CTA -> [gridDim.x, D]; the caller sums the partials.
+// Persistent CTAs: each warp strides over rows and keeps its dw/db partials in registers.
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, typename TG, typename TDx, int MAXV>
+__global__ void __launch_bounds__(kNormWarps * 32)
+norm_bwd_kernel(const TIn* __restrict__ x, const TG* __restrict__ g, const float* __restrict__ w, const float* __restrict__ mean_in,
+                const float* __restrict__ rstd_in, TDx* __restrict__ dx, float* __restrict__ dw_part, float* __restrict__ db_part,
+                long long M, int D, int rms) {
+  extern __shared__ float sm[];        // [kNormWarps][2][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float dw[MAXV][4], db[MAXV][4], wv[MAXV][4];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int d = (i * 32 + lane) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dw[i][j] = 0.f; db[i][j] = 0.f; wv[i][j] = 0.f; }
+    if (d < D) Vec4<float>::load(w + d, wv[i]);
+  }
+  for (long long row = static_cast<long long>(blockIdx.x) * kNormWarps + warp; row < M;
+       row += static_cast<long long>(gridDim.x) * kNormWarps) {
+    const float mean = rms ? 0.f : mean_in[row], rstd = rstd_in[row];
+    float xh[MAXV][4], gw[MAXV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int d = (i * 32 + lane) * 4;
+      if (d < D) {
+        float xv[4], gv[4];
+        Vec4<TIn>::load(x + row * D + d, xv);
+        Vec4<TG>::load(g + row * D + d, gv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xh[i][j] = (xv[j] - mean) * rstd;
+          gw[i][j] = gv[j] * wv[i][j];
+          dw[i][j] += gv[j] * xh[i][j];
+          db[i][j] += gv[j];
+          s1 += gw[i][j];
+          s2 += gw[i][j] * xh[i][j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xh[i][j] = 0.f; gw[i][j] = 0.f; }
+      }
+    }
+    s1 = rms ? 0.f : warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int d = (i * 32 + lane) * 4;
+      if (d < D) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = rstd * (gw[i][j] - s1 - xh[i][j] * s2);
+        Vec4<TDx>::store(dx + row * D + d, o);
+      }
+    }
+  }
+  // CTA reduction of the parameter-gradient partials
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int d = (i * 32 + lane) * 4;
+    if (d < D) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sm[(warp * 2 + 0) * D + d + j] = dw[i][j];
+        sm[(warp * 2 + 1) * D + d + j] = db[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < kNormWarps; ++wi) { a += sm[(wi * 2 + 0) * D + d]; b += sm[(wi * 2 + 1) * D + d]; }
+    dw_part[static_cast<long long>(blockIdx.x) * D + d] = a;
+    if (db_part) db_part[static_cast<long long>(blockIdx.x) * D + d] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SwiGLU gate on the fused [M, 2H] projection (columns [0,H) = w1 x, [H,2H) = w3 x), bf16.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ h13, __nv_bfloat16* __restrict__ y, long long M, int H) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (idx >= M * H) return;
+  const long long row = idx / H;
+  const int c = static_cast<int>(idx % H);
+  const uint4 a = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + c);
+  const uint4 b = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + H + c);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t ow[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]), bv = *reinterpret_cast<const __nv_bfloat162*>(&bw[j]);
+    const float a0 = __bfloat162float(av.x), a1 = __bfloat162float(av.y);
+    // silu is rounded to bf16 before the product, as the reference's two separate bf16 ops do
+    const float s0 = __bfloat162float(__float2bfloat16_rn(a0 / (1.f + __expf(-a0))));
+    const float s1 = __bfloat162float(__float2bfloat16_rn(a1 / (1.f + __expf(-a1))));
+    __nv_bfloat162 o = __floats2bfloat162_rn(s0 * __bfloat162float(bv.x), s1 * __bfloat162float(bv.y));
+    ow[j] = *reinterpret_cast<uint32_t*>(&o);
+  }
+  *reinterpret_cast<uint4*>(y + idx) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ h13, const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ dh13,
+                  long long M, int H) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (idx >= M * H) return;
+  const long long row = idx / H;
+  const int c = static_cast<int>(idx % H);
+  const uint4 a = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + c);
+  const uint4 b = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + H + c);
+  const uint4 g = *reinterpret_cast<const uint4*>(gy + idx);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, gw[4] = {g.x, g.y, g.z, g.w};
+  uint32_t da[4], db[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]), bv = *reinterpret_cast<const __nv_bfloat162*>(&bw[j]);
+    const __nv_bfloat162 gv = *reinterpret_cast<const __nv_bfloat162*>(&gw[j]);
+    float ra[2], rb[2];
+    const float aa[2] = {__bfloat162float(av.x), __bfloat162float(av.y)}, bb[2] = {__bfloat162float(bv.x), __bfloat162float(bv.y)};
+    const float gg[2] = {__bfloat162float(gv.x), __bfloat162float(gv.y)};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float sig = 1.f / (1.f + __expf(-aa[e]));
+      const float silu = aa[e] * sig;
+      ra[e] = gg[e] * bb[e] * sig * (1.f + aa[e] * (1.f - sig));
+      rb[e] = gg[e] * silu;
+    }
+    __nv_bfloat162 oa = __floats2bfloat162_rn(ra[0], ra[1]), ob = __floats2bfloat162_rn(rb[0], rb[1]);
+    da[j] = *reinterpret_cast<uint32_t*>(&oa);
+    db[j] = *reinterpret_cast<uint32_t*>(&ob);
+  }
+  *reinterpret_cast<uint4*>(dh13 + row * 2 * H + c) = make_uint4(da[0], da[1], da[2], da[3]);
+  *reinterpret_cast<uint4*>(dh13 + row * 2 * H + H + c) = make_uint4(db[0], db[1], db[2], db[3]);
+}
+
+template <typename TIn, typename TOut>
+static int launch_norm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, long long M, int D,
+                           float eps, int rms, cudaStream_t stream) {
+  const unsigned grid = static_cast<unsigned>((M + kNormWarps - 1) / kNormWarps);
+  const TIn* xi = static_cast<const TIn*>(x);
+  TOut* yo = static_cast<TOut*>(y);
+  if (D <= 128) norm_fwd_kernel<TIn, TOut, 1><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms);
+  else if (D <= 256) norm_fwd_kernel<TIn, TOut, 2><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms);
+  else if (D <= 512) norm_fwd_kernel<TIn, TOut, 4><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms);
+  else if (D <= 1024) norm_fwd_kernel<TIn, TOut, 8><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms);
+  else return FK_ERR_UNSUPPORTED;
+  return FK_OK;
+}
+
+template <typename TIn, typename TG, typename TDx>
+static int launch_norm_bwd(const void* x, const void* g, const float* w, const float* mean, const float* rstd, void* dx,
+                           float* dwp, float* dbp, long long M, int D, int rms, int grid, cudaStream_t stream) {
+  const TIn* xi = static_cast<const TIn*>(x);
+  const TG* gi = static_cast<const TG*>(g);
+  TDx* dxo = static_cast<TDx*>(dx);
+  const size_t smem = static_cast<size_t>(kNormWarps) * 2 * D * sizeof(float);
+  if (D <= 128) norm_bwd_kernel<TIn, TG, TDx, 1><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms);
+  else if (D <= 256) norm_bwd_kernel<TIn, TG, TDx, 2><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms);
+  else if (D <= 512) norm_bwd_kernel<TIn, TG, TDx, 4><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms);
+  else return FK_ERR_UNSUPPORTED;
+  return FK_OK;
+}
+
+}  // namespace fk
+
+using namespace fk;
+
+#define FK_API extern "C" __attribute__((visibility("default")))
+
+// dtype codes: 0 = f32, 1 = bf16
+FK_API int fk_norm_forward(const void* x, int x_dtype, const float* weight, const float* bias, void* y, int y_dtype,
+                           float* mean, float* rstd, long long M, int D, float eps, int rms, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(x && weight && y && rstd && M > 0 && D > 0 && D % 4 == 0, "fk_norm_forward: bad argument (D % 4 == 0)");
+  FK_REQUIRE(rms || mean, "fk_norm_forward: LayerNorm needs the mean buffer");
+  int rc = FK_ERR_UNSUPPORTED;
+  if (x_dtype == 0 && y_dtype == 1) rc = launch_norm_fwd<float, __nv_bfloat16>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream);
+  else if (x_dtype == 0 && y_dtype == 0) rc = launch_norm_fwd<float, float>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream);
+  else if (x_dtype == 1 && y_dtype == 1) rc = launch_norm_fwd<__nv_bfloat16, __nv_bfloat16>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream);
+  if (rc != FK_OK) { fk_set_last_error("fk_norm_forward: unsupported dtype combination or D > 1024", __FILE__, __LINE__); return rc; }
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+FK_API int fk_norm_backward_grid(void) { return 148 * 4; }
+
+FK_API int fk_norm_backward(const void* x, int x_dtype, const void* g, int g_dtype, const float* weight, const float* mean,
+                            const float* rstd, void* dx, int dx_dtype, float* dw_part, float* db_part, long long M, int D,
+                            int rms, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(x && g && weight && rstd && dx && dw_part && M > 0 && D > 0 && D % 4 == 0, "fk_norm_backward: bad argument");
+  FK_REQUIRE(rms || mean, "fk_norm_backward: LayerNorm needs the mean buffer");
+  const int grid = fk_norm_backward_grid();
+  int rc = FK_ERR_UNSUPPORTED;
+  if (x_dtype == 0 && g_dtype == 1 && dx_dtype == 0) rc = launch_norm_bwd<float, __nv_bfloat16, float>(x, g, weight, mean, rstd, dx, dw_part, db_part, M, D, rms, grid, stream);
+  else if (x_dtype == 0 && g_dtype == 0 && dx_dtype == 0) rc = launch_norm_bwd<float, float, float>(x, g, weight, mean, rstd, dx, dw_part, db_part, M, D, rms, grid, stream);
+  else if (x_dtype == 1 && g_dtype == 1 && dx_dtype == 1) rc = launch_norm_bwd<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(x, g, weight, mean, rstd, dx, dw_part, db_part, M, D, rms, grid, stream);
+  if (rc != FK_OK) { fk_set_last_error("fk_norm_backward: unsupported dtype combination or D > 512", __FILE__, __LINE__); return rc; }
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+FK_API int fk_swiglu_forward(const void* h13, void* y, long long M, int H, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(h13 && y && M > 0 && H > 0 && H % 8 == 0, "fk_swiglu_forward: bad argument (H % 8 == 0)");
+  const long long n = M * H / 8;
+  swiglu_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(h13),
+                                                                                static_cast<__nv_bfloat16*>(y), M, H);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+FK_API int fk_swiglu_backward(const void* h13, const void* gy, void* dh13, long long M, int H, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(h13 && gy && dh13 && M > 0 && H > 0 && H % 8 == 0, "fk_swiglu_backward: bad argument (H % 8 == 0)");
+  const long long n = M * H / 8;
+  swiglu_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(h13), static_cast<const __nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(dh13), M, H);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}

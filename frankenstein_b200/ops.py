@@ -1,0 +1,246 @@
+"""torch.autograd wrappers over the transformer-block kernels of libfk_b200.so.
+
+LayerNorm / RMSNorm, SwiGLU gate, RoPE and masked flash attention, each a thin
+``torch.autograd.Function`` that passes raw device pointers + the current stream through the C ABI
+(include/fk_b200.h).  CPU tensors raise: there is no fallback path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import FkError, check, lib, ptr, require_cuda, require_device, stream
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm / RMSNorm
+# ------------------------------------------------------------------------------------------------
+class _NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, rms, out_dtype):
+        require_cuda(x, weight)
+        require_device()
+        D = x.shape[-1]
+        xc = x.contiguous()
+        if xc.dtype not in _DT or (xc.dtype == torch.bfloat16 and out_dtype == torch.float32):
+            xc = xc.float()
+        M = xc.numel() // D
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+        mean = None if rms else torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        check(lib().fk_norm_forward(ptr(xc), _DT[xc.dtype], ptr(w), ptr(b), ptr(y), _DT[out_dtype], ptr(mean), ptr(rstd),
+                                    M, D, float(eps), int(rms), stream()), "fk_norm_forward")
+        ctx.save_for_backward(xc, w, mean if mean is not None else torch.empty(0, device=x.device), rstd)
+        ctx.rms = rms
+        ctx.has_bias = bias is not None
+        ctx.in_dtype = x.dtype
+        ctx.w_dtype = weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, w, mean, rstd = ctx.saved_tensors
+        D = xc.shape[-1]
+        M = xc.numel() // D
+        g = g.contiguous()
+        # supported (x, g, dx) combinations of the kernel
+        if xc.dtype == torch.float32 and g.dtype not in _DT:
+            g = g.float()
+        if xc.dtype == torch.bfloat16 and g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        dx = torch.empty_like(xc)
+        nb = lib().fk_norm_backward_grid()
+        dwp = torch.empty(nb, D, device=xc.device, dtype=torch.float32)
+        dbp = torch.empty(nb, D, device=xc.device, dtype=torch.float32) if ctx.has_bias else None
+        check(lib().fk_norm_backward(ptr(xc), _DT[xc.dtype], ptr(g), _DT[g.dtype], ptr(w), ptr(mean) if not ctx.rms else 0,
+                                     ptr(rstd), ptr(dx), _DT[dx.dtype], ptr(dwp), ptr(dbp), M, D, int(ctx.rms), stream()),
+              "fk_norm_backward")
+        dw = dwp.sum(0).to(ctx.w_dtype)
+        db = dbp.sum(0).to(ctx.w_dtype) if ctx.has_bias else None
+        return dx.to(ctx.in_dtype), dw, db, None, None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5, out_dtype=torch.bfloat16):
+    return _NormFn.apply(x, weight, bias, eps, False, out_dtype)
+
+
+def rms_norm(x, weight, eps=1e-6, out_dtype=torch.bfloat16):
+    return _NormFn.apply(x, weight, None, eps, True, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# SwiGLU gate on the fused [.., 2H] projection
+# ------------------------------------------------------------------------------------------------
+class _SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h13):
+        require_cuda(h13)
+        require_device()
+        if h13.dtype != torch.bfloat16:
+            raise FkError("swiglu expects the bf16 fused projection")
+        h13 = h13.contiguous()
+        H = h13.shape[-1] // 2
+        M = h13.numel() // (2 * H)
+        y = torch.empty(*h13.shape[:-1], H, device=h13.device, dtype=torch.bfloat16)
+        check(lib().fk_swiglu_forward(ptr(h13), ptr(y), M, H, stream()), "fk_swiglu_forward")
+        ctx.save_for_backward(h13)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (h13,) = ctx.saved_tensors
+        H = h13.shape[-1] // 2
+        M = h13.numel() // (2 * H)
+        gy = gy.contiguous().to(torch.bfloat16)
+        d = torch.empty_like(h13)
+        check(lib().fk_swiglu_backward(ptr(h13), ptr(gy), ptr(d), M, H, stream()), "fk_swiglu_backward")
+        return d
+
+
+def swiglu(h13):
+    return _SwiGLUFn.apply(h13)
+
+
+# ------------------------------------------------------------------------------------------------
+# mask labels and RoPE description
+# ------------------------------------------------------------------------------------------------
+class LabelMask:
+    """key j visible to query i  <=>  kid[b, j] <= qid[b, i].  Holds the per-tile label ranges, computed once
+    and shared by every layer of a forward pass."""
+
+    def __init__(self, qid: torch.Tensor, kid: Optional[torch.Tensor] = None):
+        require_cuda(qid)
+        self.qid = qid.to(torch.int32).contiguous()
+        self.kid = self.qid if kid is None else kid.to(torch.int32).contiguous()
+        self.qmin, self.qmax = self._ranges(self.qid)
+        if self.kid is self.qid:
+            self.kmin, self.kmax = self.qmin, self.qmax
+        else:
+            self.kmin, self.kmax = self._ranges(self.kid)
+
+    @staticmethod
+    def _ranges(ids):
+        B, S = ids.shape
+        nt = (S + 63) // 64
+        lo = torch.empty(B, nt, device=ids.device, dtype=torch.int32)
+        hi = torch.empty(B, nt, device=ids.device, dtype=torch.int32)
+        check(lib().fk_attn_label_ranges(ptr(ids), B, S, ptr(lo), ptr(hi), stream()), "fk_attn_label_ranges")
+        return lo, hi
+
+    @staticmethod
+    def block_causal(B: int, S: int, tokens_per_block: int, device) -> "LabelMask":
+        """brainformer.py:93-111 build_advanced_causal_mask: attend iff block(k) <= block(q)."""
+        ids = (torch.arange(S, device=device, dtype=torch.int32) // tokens_per_block)[None].expand(B, S)
+        return LabelMask(ids.contiguous())
+
+    @staticmethod
+    def padding(is_padded: torch.Tensor) -> "LabelMask":
+        """simple_mae:349-352: attend iff neither the query nor the key is a padded token."""
+        big = torch.iinfo(torch.int32).max
+        kid = torch.where(is_padded, big, 0).to(torch.int32)
+        qid = torch.where(is_padded, -1, 0).to(torch.int32)
+        return LabelMask(qid, kid)
+
+    def dense(self) -> torch.Tensor:
+        """[B, 1, Sq, Sk] bool, True = attend (only for tests / the library-SDPA compatibility path)."""
+        return (self.kid[:, None, None, :] <= self.qid[:, None, :, None])
+
+
+class RopeSpec:
+    """table: fp32 [P, hd/2, 2] (cos, sin) = view_as_real(build_complex_rope_cache(...)); position of token
+    (b, s) = pos[b, s] if pos is given else s + offset."""
+
+    def __init__(self, table: torch.Tensor, pos: Optional[torch.Tensor] = None, offset: int = 0):
+        self.table = table.contiguous()
+        self.pos = None if pos is None else pos.to(torch.int32).contiguous()
+        self.offset = int(offset)
+
+    @staticmethod
+    def from_complex(cache: torch.Tensor, T: int, last: bool = True) -> "RopeSpec":
+        """cache [P, hd/2] complex64; brainformer slices rope[-T:] (last=True), simple_mae rope[:T]."""
+        table = torch.view_as_real(cache).float().contiguous()
+        return RopeSpec(table, None, cache.shape[0] - T if last else 0)
+
+
+def _rope_inplace(x4, spec: RopeSpec, inverse: bool):
+    """x4: bf16 view [B, S, H, 32] (token stride arbitrary, head stride 32)."""
+    B, S, H, hd = x4.shape
+    assert x4.stride(3) == 1 and x4.stride(2) == hd
+    check(lib().fk_rope(ptr(x4), x4.stride(0), x4.stride(1), B, S, H, hd, ptr(spec.table), spec.table.shape[0],
+                        ptr(spec.pos), spec.offset, int(inverse), stream()), "fk_rope")
+
+
+# ------------------------------------------------------------------------------------------------
+# attention on the fused QKV projection
+# ------------------------------------------------------------------------------------------------
+class _AttnQKVFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, n_heads, rope, mask, scale):
+        """qkv: bf16 [B, S, 3*H*32] fresh output of the fused projection (q|k|v); RoPE is applied in place."""
+        require_cuda(qkv)
+        require_device()
+        if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous():
+            raise FkError("attention expects a contiguous bf16 QKV buffer")
+        B, S, W = qkv.shape
+        H = n_heads
+        hd = W // (3 * H)
+        v5 = qkv.view(B, S, 3, H, hd)
+        q, k, v = v5[:, :, 0], v5[:, :, 1], v5[:, :, 2]
+        if rope is not None:
+            _rope_inplace(q, rope, False)
+            _rope_inplace(k, rope, False)
+        out = torch.empty(B, S, H * hd, device=qkv.device, dtype=torch.bfloat16)
+        need_grad = qkv.requires_grad
+        lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+        m = mask
+        check(lib().fk_attn_forward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, S, hd,
+                                    q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                    out.stride(0), out.stride(1),
+                                    ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0,
+                                    ptr(m.qmax) if m else 0, ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0,
+                                    float(scale), stream()), "fk_attn_forward")
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.rope, ctx.mask, ctx.scale, ctx.H = rope, mask, scale, H
+        return out
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, out, lse = ctx.saved_tensors
+        B, S, W = qkv.shape
+        H = ctx.H
+        hd = W // (3 * H)
+        d_o = d_o.contiguous().to(torch.bfloat16)
+        v5 = qkv.view(B, S, 3, H, hd)
+        q, k, v = v5[:, :, 0], v5[:, :, 1], v5[:, :, 2]
+        dqkv = torch.empty_like(qkv)
+        d5 = dqkv.view(B, S, 3, H, hd)
+        dq, dk, dv = d5[:, :, 0], d5[:, :, 1], d5[:, :, 2]
+        delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+        m = ctx.mask
+        check(lib().fk_attn_backward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv),
+                                     B, H, S, S, hd, q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                     out.stride(0), out.stride(1), d_o.stride(0), d_o.stride(1),
+                                     dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
+                                     ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0,
+                                     ptr(m.qmax) if m else 0, ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0,
+                                     float(ctx.scale), stream()), "fk_attn_backward")
+        if ctx.rope is not None:
+            _rope_inplace(dq, ctx.rope, True)
+            _rope_inplace(dk, ctx.rope, True)
+        return dqkv, None, None, None, None
+
+
+def attention_qkv(qkv, n_heads: int, rope: Optional[RopeSpec] = None, mask: Optional[LabelMask] = None,
+                  scale: Optional[float] = None):
+    """softmax(q k^T * scale + mask) v over the fused QKV buffer -> [B, S, H*32] bf16."""
+    hd = qkv.shape[-1] // (3 * n_heads)
+    if hd != 32:
+        raise FkError("the attention kernel is built for head_dim 32")
+    if scale is None:
+        scale = hd ** -0.5
+    return _AttnQKVFn.apply(qkv, n_heads, rope, mask, scale)

@@ -96,6 +96,41 @@ int fk_masked_l1_forward(const void* pred, int dtype, const float* gt, long long
 int fk_masked_l1_backward(const void* pred, int dtype, const float* gt, const unsigned char* row_valid,
                           const float* g_loss, const float* denom, long long R, int C, void* grad_pred, void* stream);
 
+/* ---- transformer blocks (models/brainformer.py, models/simple_mae) ---------------------------- */
+/* nn.LayerNorm (brainformer.py:237-239,287) / RMSNorm (simple_mae:181-192).  dtype codes 0=f32 1=bf16.
+ * Supported (x, y): (f32,bf16) (f32,f32) (bf16,bf16).  mean/rstd: [M] fp32 saved for backward (mean unused for rms). */
+int fk_norm_forward(const void* x, int x_dtype, const float* weight, const float* bias, void* y, int y_dtype,
+                    float* mean, float* rstd, long long M, int D, float eps, int rms, void* stream);
+/* dw_part/db_part: [fk_norm_backward_grid(), D] partial sums (caller reduces over dim 0).
+ * Supported (x, g, dx): (f32,bf16,f32) (f32,f32,f32) (bf16,bf16,bf16). */
+int fk_norm_backward_grid(void);
+int fk_norm_backward(const void* x, int x_dtype, const void* g, int g_dtype, const float* weight, const float* mean,
+                     const float* rstd, void* dx, int dx_dtype, float* dw_part, float* db_part, long long M, int D,
+                     int rms, void* stream);
+/* MLP gate silu(w1 x) * (w3 x) (brainformer.py:123-124) on the fused bf16 projection h13 [M, 2H]. */
+int fk_swiglu_forward(const void* h13, void* y, long long M, int H, void* stream);
+int fk_swiglu_backward(const void* h13, const void* gy, void* dh13, long long M, int H, void* stream);
+/* apply_rope (brainformer.py:70-91) in place on bf16 [B,S,H,32] (strides in elements); table [P,16,2] fp32
+ * (cos,sin) = view_as_real(build_complex_rope_cache); pos (nullable) [B,S] int32 else position = s + pos_offset. */
+int fk_rope(void* x, long long bs, long long ts, int B, int S, int H, int head_dim, const float* table, int P,
+            const int* pos, int pos_offset, int inverse, void* stream);
+/* F.scaled_dot_product_attention(q,k,v,attn_mask) (brainformer.py:168,215) with the mask given as integer labels:
+ * key j visible to query i  <=>  kid[b][j] <= qid[b][i]  (null = no mask).  q/k/v/out: bf16 [B,S,H,32] with
+ * batch/token strides in elements.  qmin..kmax: per-64-token-tile label ranges from fk_attn_label_ranges.
+ * lse: [B,H,Sq] fp32 (log2 domain), nullable in inference. */
+int fk_attn_label_ranges(const int* ids, int B, int S, int* tmin, int* tmax, void* stream);
+int fk_attn_forward(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int Sq, int Sk,
+                    int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
+                    long long v_ts, long long o_bs, long long o_ts, const int* qid, const int* kid, const int* qmin,
+                    const int* qmax, const int* kmin, const int* kmax, float scale, void* stream);
+/* delta: [B,H,Sq] fp32 workspace.  dq/dk/dv: bf16, same addressing scheme as q/k/v. */
+int fk_attn_backward(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                     float* delta, void* dq, void* dk, void* dv, int B, int H, int Sq, int Sk, int head_dim,
+                     long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs, long long v_ts,
+                     long long o_bs, long long o_ts, long long do_bs, long long do_ts, long long dq_bs, long long dq_ts,
+                     long long dk_bs, long long dk_ts, long long dv_bs, long long dv_ts, const int* qid, const int* kid,
+                     const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
