@@ -111,3 +111,47 @@ def reset_launch_count() -> None:
 
 
 DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+# ------------------------------------------------------------------------------------------------
+# optional per-kernel timing (bench.py): CUDA events recorded on the launching stream around a call
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """`with timed("name", work): ...` records two events on the current stream when enabled; `summary()`
+    synchronises and returns {name: (launches, total_ms, total_work)}.  Disabled = zero overhead."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def reset(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b, work in self.records:
+            n, ms, w = out.get(name, (0, 0.0, 0.0))
+            out[name] = (n + 1, ms + a.elapsed_time(b), w + work)
+        return out
+
+
+TIMER = KernelTimer()
+
+
+class timed:
+    def __init__(self, name, work=0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if TIMER.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMER.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            TIMER.records.append((self.name, self.a, b, self.work))
+        return False

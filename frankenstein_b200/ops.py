@@ -10,7 +10,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import FkError, check, lib, ptr, require_cuda, require_device, stream
+from ._lib import FkError, check, lib, ptr, require_cuda, require_device, stream, timed
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
@@ -198,7 +198,8 @@ class _AttnQKVFn(torch.autograd.Function):
         need_grad = qkv.requires_grad
         lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
         m = mask
-        check(lib().fk_attn_forward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, S, hd,
+        with timed("attn_fwd", 4.0 * B * H * S * S * hd):
+          check(lib().fk_attn_forward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, S, hd,
                                     q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                                     out.stride(0), out.stride(1),
                                     ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0,
@@ -222,7 +223,8 @@ class _AttnQKVFn(torch.autograd.Function):
         dq, dk, dv = d5[:, :, 0], d5[:, :, 1], d5[:, :, 2]
         delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
         m = ctx.mask
-        check(lib().fk_attn_backward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv),
+        with timed("attn_bwd", 14.0 * B * H * S * S * hd):
+          check(lib().fk_attn_backward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv),
                                      B, H, S, S, hd, q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                                      out.stride(0), out.stride(1), d_o.stride(0), d_o.stride(1),
                                      dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),

@@ -22,7 +22,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import _lib
-from ._lib import DTYPE_CODE, FkError, check, lib, ptr, require_cuda, require_device, stream
+from ._lib import DTYPE_CODE, FkError, check, lib, ptr, require_cuda, require_device, stream, timed
 
 BN = 128  # code tile of the search kernel (c2 padding granularity)
 CAND = 4  # candidates per (row, slot) written by the search kernel
@@ -79,8 +79,9 @@ def search(xb: torch.Tensor, cb: torch.Tensor, c2pad: torch.Tensor, K: int, use_
     S = lib().fk_vq_search_slots(N, K, max_ctas)
     cand_val = torch.empty(N, S, CAND, device=xb.device, dtype=torch.float32)
     cand_idx = torch.empty(N, S, CAND, device=xb.device, dtype=torch.int32)
-    check(lib().fk_vq_search(ptr(xb), ptr(cb), ptr(c2pad), N, K, Dp, int(use_cosine), ptr(cand_val), ptr(cand_idx), S,
-                             max_ctas, stream()), "fk_vq_search")
+    with timed("vq_search", 2.0 * N * K * Dp):
+        check(lib().fk_vq_search(ptr(xb), ptr(cb), ptr(c2pad), N, K, Dp, int(use_cosine), ptr(cand_val), ptr(cand_idx), S,
+                                 max_ctas, stream()), "fk_vq_search")
     return cand_val, cand_idx
 
 

@@ -152,3 +152,32 @@ def simple_mae_forward(sd, x, enc_cfg, dec_cfg, masked_indices, unmasked_indices
     pm, xm = pred[rows, masked_indices], x[rows, masked_indices]
     valid = ~is_padded[rows, masked_indices]
     return F.mse_loss(pm, xm, reduction="none")[valid.nonzero(as_tuple=True)].mean(), pred
+
+
+def cross_attention(sd, pre, x, context, n_heads):
+    """CausalCrossAttention.forward (models/brainformer.py:200-219), no mask."""
+    B, T, _ = x.shape
+    S = context.shape[1]
+    q = F.linear(x, sd[f"{pre}.qw.weight"]).view(B, T, n_heads, -1).transpose(1, 2)
+    k = F.linear(context, sd[f"{pre}.kw.weight"]).view(B, S, n_heads, -1).transpose(1, 2)
+    v = F.linear(context, sd[f"{pre}.vw.weight"]).view(B, S, n_heads, -1).transpose(1, 2)
+    res = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, -1)
+    return F.linear(res, sd[f"{pre}.project.weight"])
+
+
+def brainformer_forward(sd, x, enc_cfg, cfg, targets=None):
+    """BrainFormer.forward (models/brainformer.py:532-558): encoder -> perceiver CrossBlocks -> ln_f -> to_motion -> L1."""
+    ctx = encoder_forward(sd, x, enc_cfg, pre="encoder.")
+    b = x.shape[0]
+    h = sd["learnable_queries"].expand(b, -1, -1)
+    rope = rope_cache(cfg["head_dim"], cfg["n_output_tokens"], cfg.get("rope_theta", 10000))
+    for i in range(n_layers(sd, "perceiver.h.")):
+        p = f"perceiver.h.{i}"
+        # CrossBlock.forward (models/brainformer.py:257-268)
+        h = h + cross_attention(sd, f"{p}.cross_attn", _norm(sd, f"{p}.ln_1", h, False), ctx, cfg["n_heads"])
+        h = h + mlp(sd, f"{p}.mlp", _norm(sd, f"{p}.ln_2", h, False))
+        h = block(sd, f"{p}.sa_block", h, cfg["n_heads"], None, rope)
+    pred = F.linear(_norm(sd, "perceiver.ln_f", h, False), sd["perceiver.to_motion.weight"], sd["perceiver.to_motion.bias"])
+    if targets is None:
+        return None, pred
+    return F.l1_loss(pred, targets), pred
