@@ -84,6 +84,12 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// 2^x on the SFU (ex2.approx.ftz): one MUFU, no range fix-up code around it
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -137,7 +143,7 @@ __device__ __forceinline__ void mma_p_tile(float (&out)[4][4], const float (&pac
 // ------------------------------------------------------------------------------------------------
 // forward.  grid = (ceil(Sq/128), H, B)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, 3)
 attn_fwd_kernel(const AttnParams p) {
   __shared__ __align__(128) uint8_t sQ[kTQ * 64];
   __shared__ __align__(128) uint8_t sK[2][kTK * 64];
@@ -212,33 +218,35 @@ attn_fwd_kernel(const AttnParams p) {
     mma_a_tileT(s, qa, smem_u32(sK[buf]));
 
     const bool need_mask = (masked && p.kmax[b * nkt64 + kt] > tq_min) || (kt * kTK + kTK > p.Sk);
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (need_mask) {           // warp-uniform: only tiles that straddle a label boundary (or the ragged tail) pay for it
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float v = s[nt][e] * p.scale_log2;
-        if (need_mask) {
+        for (int e = 0; e < 4; ++e) {
           const int col = nt * 8 + t4 * 2 + (e & 1);
           const int kid = masked ? sKid[buf][col] : ((kt * kTK + col < p.Sk) ? 0 : 0x7fffffff);
           const int qid = masked ? ((e & 2) ? qid1 : qid0) : 0;
-          if (kid > qid) v = -INFINITY;
+          if (kid > qid) s[nt][e] = -INFINITY;
         }
-        s[nt][e] = v;
       }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    // running maxima live in the scaled log2 domain; the raw scores are scaled inside the exp2 FFMA
+    const float mn0 = fmaxf(m0, mx0 * p.scale_log2), mn1 = fmaxf(m1, mx1 * p.scale_log2);
     const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0, ms1 = (mn1 == -INFINITY) ? 0.f : mn1;
-    const float al0 = exp2f(m0 - ms0), al1 = exp2f(m1 - ms1);
+    const float al0 = fast_exp2(m0 - ms0), al1 = fast_exp2(m1 - ms1);
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - ms0); s[nt][1] = exp2f(s[nt][1] - ms0);
-      s[nt][2] = exp2f(s[nt][2] - ms1); s[nt][3] = exp2f(s[nt][3] - ms1);
+      s[nt][0] = fast_exp2(fmaf(s[nt][0], p.scale_log2, -ms0)); s[nt][1] = fast_exp2(fmaf(s[nt][1], p.scale_log2, -ms0));
+      s[nt][2] = fast_exp2(fmaf(s[nt][2], p.scale_log2, -ms1)); s[nt][3] = fast_exp2(fmaf(s[nt][3], p.scale_log2, -ms1));
       rs0 += s[nt][0] + s[nt][1];
       rs1 += s[nt][2] + s[nt][3];
     }
@@ -300,7 +308,7 @@ attn_delta_kernel(const AttnParams p) {
 // ------------------------------------------------------------------------------------------------
 // dQ.  grid = (ceil(Sq/128), H, B); same loop structure as the forward.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_bwd_dq_kernel(const AttnParams p) {
   __shared__ __align__(128) uint8_t sQ[kTQ * 64];
   __shared__ __align__(128) uint8_t sDO[kTQ * 64];
@@ -377,20 +385,25 @@ attn_bwd_dq_kernel(const AttnParams p) {
     mma_a_tileT(s, qa, smem_u32(sK[buf]));
     mma_a_tileT(dp, doa, smem_u32(sV[buf]));
     const bool need_mask = (masked && p.kmax[b * nkt64 + kt] > tq_min) || (kt * kTK + kTK > p.Sk);
+    if (need_mask) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float lse = (e & 2) ? lse1 : lse0, dl = (e & 2) ? dl1 : dl0;
-        float pv = exp2f(s[nt][e] * p.scale_log2 - lse);
-        if (need_mask) {
+        for (int e = 0; e < 4; ++e) {
           const int col = nt * 8 + t4 * 2 + (e & 1);
           const int kid = masked ? sKid[buf][col] : ((kt * kTK + col < p.Sk) ? 0 : 0x7fffffff);
           const int qid = masked ? ((e & 2) ? qid1 : qid0) : 0;
-          if (kid > qid) pv = 0.f;
+          if (kid > qid) s[nt][e] = -INFINITY;                 // exp2(-inf) = 0
         }
-        s[nt][e] = pv * (dp[nt][e] - dl) * p.scale;     // dS
       }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      // dS / scale = P * (dP - delta); the softmax scale is applied once to the dQ accumulators at the end
+      s[nt][0] = fast_exp2(fmaf(s[nt][0], p.scale_log2, -lse0)) * (dp[nt][0] - dl0);
+      s[nt][1] = fast_exp2(fmaf(s[nt][1], p.scale_log2, -lse0)) * (dp[nt][1] - dl0);
+      s[nt][2] = fast_exp2(fmaf(s[nt][2], p.scale_log2, -lse1)) * (dp[nt][2] - dl1);
+      s[nt][3] = fast_exp2(fmaf(s[nt][3], p.scale_log2, -lse1)) * (dp[nt][3] - dl1);
     }
     mma_p_tile(dq, s, smem_u32(sK[buf]));
     __syncthreads();
@@ -401,8 +414,8 @@ attn_bwd_dq_kernel(const AttnParams p) {
 #pragma unroll
   for (int dt = 0; dt < 4; ++dt) {
     const int col = dt * 8 + t4 * 2;
-    if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(og + static_cast<long long>(r0) * p.dq_ts + col) = pack_bf16(dq[dt][0], dq[dt][1]);
-    if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(og + static_cast<long long>(r1) * p.dq_ts + col) = pack_bf16(dq[dt][2], dq[dt][3]);
+    if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(og + static_cast<long long>(r0) * p.dq_ts + col) = pack_bf16(dq[dt][0] * p.scale, dq[dt][1] * p.scale);
+    if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(og + static_cast<long long>(r1) * p.dq_ts + col) = pack_bf16(dq[dt][2] * p.scale, dq[dt][3] * p.scale);
   }
 }
 
@@ -410,14 +423,14 @@ attn_bwd_dq_kernel(const AttnParams p) {
 // dK, dV.  grid = (ceil(Sk/128), H, B): the CTA owns 128 keys (8 warps x 16) and streams 64-query
 // tiles.  Everything is computed transposed (S^T = K Q^T), so P^T and dS^T are already A operands.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_bwd_dkv_kernel(const AttnParams p) {
   __shared__ __align__(128) uint8_t sK[kTQ * 64];
   __shared__ __align__(128) uint8_t sV[kTQ * 64];
   __shared__ __align__(128) uint8_t sQ[2][kTK * 64];
   __shared__ __align__(128) uint8_t sDO[2][kTK * 64];
   __shared__ int sQid[2][kTK];
-  __shared__ float sLse[2][kTK], sDelta[2][kTK];
+  __shared__ __align__(8) float sLse[2][kTK], sDelta[2][kTK];
   const int kt128 = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const int k0 = kt128 * kTQ;
@@ -485,18 +498,32 @@ attn_bwd_dkv_kernel(const AttnParams p) {
       for (int j = 0; j < 4; ++j) { st[i][j] = 0.f; dpt[i][j] = 0.f; }
     mma_a_tileT(st, ka, smem_u32(sQ[buf]));        // S^T[key, q]
     mma_a_tileT(dpt, va, smem_u32(sDO[buf]));      // dP^T[key, q] = V dO^T
-    // element masking is always evaluated here: out-of-range keys / queries carry sentinel labels
+    // label compare only where the tile pair straddles a boundary; out-of-range queries have lse = +inf (P = 0),
+    // out-of-range keys only produce rows that are never stored
+    const bool need_mask = masked && (tk_max > p.qmin[b * nqt + qt]);
+    if (need_mask) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + t4 * 2 + (e & 1);
+          if (((e & 2) ? kid1 : kid0) > sQid[buf][col]) st[nt][e] = -INFINITY;
+        }
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = nt * 8 + t4 * 2 + (e & 1);
-        const int kid = (e & 2) ? kid1 : kid0;
-        float pv = exp2f(st[nt][e] * p.scale_log2 - sLse[buf][col]);
-        if (kid > sQid[buf][col]) pv = 0.f;
-        st[nt][e] = pv;                                                   // P^T
-        dpt[nt][e] = pv * (dpt[nt][e] - sDelta[buf][col]) * p.scale;      // dS^T
-      }
+      const int col = nt * 8 + t4 * 2;
+      const float2 ls = *reinterpret_cast<const float2*>(&sLse[buf][col]);
+      const float2 dl = *reinterpret_cast<const float2*>(&sDelta[buf][col]);
+      st[nt][0] = fast_exp2(fmaf(st[nt][0], p.scale_log2, -ls.x));       // P^T
+      st[nt][1] = fast_exp2(fmaf(st[nt][1], p.scale_log2, -ls.y));
+      st[nt][2] = fast_exp2(fmaf(st[nt][2], p.scale_log2, -ls.x));
+      st[nt][3] = fast_exp2(fmaf(st[nt][3], p.scale_log2, -ls.y));
+      dpt[nt][0] = st[nt][0] * (dpt[nt][0] - dl.x);                      // dS^T / scale
+      dpt[nt][1] = st[nt][1] * (dpt[nt][1] - dl.y);
+      dpt[nt][2] = st[nt][2] * (dpt[nt][2] - dl.x);
+      dpt[nt][3] = st[nt][3] * (dpt[nt][3] - dl.y);
     }
     mma_p_tile(dv, st, smem_u32(sDO[buf]));        // dV += P^T dO
     mma_p_tile(dk, dpt, smem_u32(sQ[buf]));        // dK += dS^T Q
@@ -510,11 +537,11 @@ attn_bwd_dkv_kernel(const AttnParams p) {
   for (int dt = 0; dt < 4; ++dt) {
     const int col = dt * 8 + t4 * 2;
     if (kr0 < p.Sk) {
-      *reinterpret_cast<uint32_t*>(dkg + static_cast<long long>(kr0) * p.dk_ts + col) = pack_bf16(dk[dt][0], dk[dt][1]);
+      *reinterpret_cast<uint32_t*>(dkg + static_cast<long long>(kr0) * p.dk_ts + col) = pack_bf16(dk[dt][0] * p.scale, dk[dt][1] * p.scale);
       *reinterpret_cast<uint32_t*>(dvg + static_cast<long long>(kr0) * p.dv_ts + col) = pack_bf16(dv[dt][0], dv[dt][1]);
     }
     if (kr1 < p.Sk) {
-      *reinterpret_cast<uint32_t*>(dkg + static_cast<long long>(kr1) * p.dk_ts + col) = pack_bf16(dk[dt][2], dk[dt][3]);
+      *reinterpret_cast<uint32_t*>(dkg + static_cast<long long>(kr1) * p.dk_ts + col) = pack_bf16(dk[dt][2] * p.scale, dk[dt][3] * p.scale);
       *reinterpret_cast<uint32_t*>(dvg + static_cast<long long>(kr1) * p.dv_ts + col) = pack_bf16(dv[dt][2], dv[dt][3]);
     }
   }
