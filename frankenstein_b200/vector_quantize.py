@@ -120,6 +120,13 @@ def ema_stats(xn, indices, K: int, extra_rows: int = 0) -> torch.Tensor:
     return stats
 
 
+def dead_code_layout(K: int, N: int, world: int):
+    """(rows contributed per rank, total candidate rows R) of the dead-code tail of the packed EMA buffer:
+    R = min(K, N * world) rounded down to a multiple of `world`, at least one row per rank."""
+    per_rank = max(1, min(K, N * world) // world)
+    return per_rank, per_rank * world
+
+
 class _VQFunction(torch.autograd.Function):
     """(quantize_out, indices, loss) = f(x); backward = fk_vq_backward (STE + commitment term + normalize Jacobian)."""
 
@@ -326,8 +333,7 @@ class VectorQuantize(nn.Module):
         # embed_sum, bins and the replacement rows (each rank fills its own slice, the SUM gathers them).
         R = 0
         if thr > 0:
-            per_rank = max(1, min(K, N * world) // world)
-            R = per_rank * world
+            per_rank, R = dead_code_layout(K, N, world)
         stats = ema_stats(xn, indices, K, extra_rows=R)
         tail = None
         if R > 0:

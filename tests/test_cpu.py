@@ -1,0 +1,99 @@
+"""CPU: the C-ABI library loads and exports every symbol of include/fk_b200.h, the host-side mirrors keep the
+reference's state-dict keys / parameter counts / mask + rope conventions, and the product path refuses CPU tensors."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    from frankenstein_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 30
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(L, name), f"{name} declared in include/fk_b200.h but not exported"
+    L2 = _lib.lib()
+    assert L2.fk_abi_version() == 1 and L2.fk_target_sm() == 100
+    assert L2.fk_last_error() is not None
+
+
+def test_host_helpers_without_gpu():
+    from frankenstein_b200 import _lib
+    L = _lib.lib()
+    # slots: 2 column halves x number of CTAs that can touch one row block
+    assert L.fk_vq_search_slots(16384, 8192, 148) == 8
+    assert L.fk_vq_search_slots(256, 128, 148) == 2
+    assert L.fk_vq_finish_partials(17) == 3 and L.fk_masked_l1_partials(16) == 2
+    assert L.fk_norm_backward_grid() == 592
+    if not torch.cuda.is_available():
+        assert L.fk_device_ok() == 0
+    # argument validation happens before any CUDA call
+    assert L.fk_vq_search(None, None, None, 0, 0, 64, 0, None, None, 1, 0, None) == -1
+    assert b"fk_vq_search" in L.fk_last_error()
+
+
+def test_dead_code_layout():
+    from frankenstein_b200.vector_quantize import dead_code_layout
+    assert dead_code_layout(8192, 16384, 1) == (8192, 8192)
+    assert dead_code_layout(8192, 16384, 8) == (1024, 8192)
+    assert dead_code_layout(512, 100, 2) == (100, 200)
+    assert dead_code_layout(10, 3, 4) == (2, 8)
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from frankenstein_b200._lib import FkError
+    from frankenstein_b200.vector_quantize import VectorQuantize
+    from frankenstein_b200 import brainformer as bf
+    with pytest.raises(FkError):
+        VectorQuantize(dim=64, codebook_size=16)(torch.zeros(1, 4, 64))
+    enc = bf.Encoder(bf.MAEConfig(window_size=64, n_electrodes=8, patch_size=8, dim=64, n_layers=1, head_dim=32, hidden_dim=64,
+                                  n_heads=2, n_kv_heads=2))
+    with pytest.raises(Exception):
+        enc(torch.zeros(1, 64, 8))
+
+
+def test_state_dict_keys_match_reference_checkpoints():
+    from frankenstein_b200 import brainformer as bf
+    from frankenstein_b200 import simple_mae as sm
+    from frankenstein_b200.vq_brain import SoundStream
+    g = torch.load(os.path.join(GOLD, "soundstream_cosine.pt"), weights_only=False)
+    m = SoundStream(**g["config"])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in g["state_dict"].items()}
+    m.load_state_dict(g["state_dict"], strict=True)
+    b = torch.load(os.path.join(GOLD, "brainformer_small.pt"), weights_only=False)
+    enc = bf.Encoder(bf.MAEConfig(**b["enc_config"]))
+    enc.load_state_dict(b["enc_state"], strict=True)
+    mae = bf.MAE(bf.MAEConfig(**b["enc_config"]))
+    mae.load_state_dict(b["mae_state"], strict=True)
+    full = bf.BrainFormer(bf.Config(encoder=bf.MAEConfig(**b["enc_config"]), **b["per_config"]))
+    full.load_state_dict(b["full_state"], strict=True)
+    s = torch.load(os.path.join(GOLD, "simple_mae_small.pt"), weights_only=False)
+    smae = sm.SimpleMAE(sm.SimpleEncoderConfig(**s["enc_config"]), sm.SimpleMAEConfig(**s["mae_config"]))
+    smae.load_state_dict(s["state"], strict=True)
+
+
+def test_known_answers():
+    """5.61M / 4.27M / 6.32M parameters, [6144,6144] mask, mask(6,2) and rope micro-vectors."""
+    from frankenstein_b200 import brainformer as bf
+    from frankenstein_b200.vq_brain import SoundStream
+    b = torch.load(os.path.join(GOLD, "brainformer_small.pt"), weights_only=False)
+    ss = SoundStream(C=256, D=64, codebook_size=1024, n_electrodes=512)
+    assert round(sum(p.numel() for p in ss.parameters()) / 1e6, 2) == 5.61
+    mc = bf.MAEConfig(window_size=768, patch_size=32)
+    enc = bf.Encoder(mc)
+    assert enc.get_num_params() == b["params_encoder_768_32"] and round(enc.get_num_params() / 1e6, 2) == 4.27
+    assert tuple(enc.attn_mask.shape) == (6144, 6144)
+    full = bf.BrainFormer(bf.Config(encoder=mc, n_output_tokens=32, output_dim=768))
+    assert round(full.get_num_params() / 1e6, 2) == 6.32
+    assert torch.equal(bf.build_advanced_causal_mask(6, 2), b["mask_6_2"])
+    assert torch.allclose(torch.view_as_real(bf.build_complex_rope_cache(8, 5, 10000)), b["rope_8_5"])
+    assert torch.allclose(bf.apply_rope(b["rope_in"], bf.build_complex_rope_cache(8, 5, 10000)), b["rope_out"])
+    x = torch.arange(2 * 16 * 4, dtype=torch.float32).view(2, 16, 4)
+    small = bf.Encoder(bf.MAEConfig(window_size=16, n_electrodes=4, patch_size=8, dim=32, n_layers=1, head_dim=32, hidden_dim=32,
+                                    n_heads=1, n_kv_heads=1))
+    from oracle.brainformer_ref import to_patches
+    assert torch.equal(small.to_patches(x), to_patches(x, 8))
