@@ -34,6 +34,8 @@ TRIALS_PER_GPU = 128
 T_BINS, N_CH = 512, 512
 VQ_K, VQ_D, VQ_C = 8192, 256, 256
 CPU_SAMPLE_TRIALS = 2
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {"vq_search": 12660480}
 
 
 def model_configs():
@@ -302,22 +304,36 @@ def main():
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)       # kernel timed inside a long step -> sustained figure
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         n_vq = B * (T_BINS // 4)
-        roof, kern = None, {}
-        if "vq_search" in ksum:
-            n, ms, _ = ksum["vq_search"]
-            flops = 2.0 * n_vq * VQ_K * VQ_D
-            ach = flops / (ms / n * 1e-3) / 1e12
-            roof = {"kernel": "vq_search_kernel (tcgen05/TMEM/TMA nearest-codeword search)", "bound": "tensor", "achieved": ach,
-                    "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
-                    "algorithmic_flops_per_launch": flops, "avg_launch_ms": ms / n, "launches_timed": n, "peak_source": peak_src}
-        dens = (16 + 1) / (2.0 * 16)                                   # block-causal density, 16 time patches
-        S = 4096
-        att = 4.0 * B * 16 * S * S * 32 * dens
-        for name, mult in (("attn_fwd", 1.0), ("attn_bwd", 2.5)):
-            if name in ksum:
-                n, ms, _ = ksum[name]
-                # only the encoder's big launches dominate; the perceiver self-attention uses library SDPA
-                kern[name] = {"launches": n, "avg_ms": ms / n, "algorithmic_tflops": att * mult / (ms / n * 1e-3) / 1e12}
+        # ---- per-kernel rooflines from CUDA events recorded around each launch inside the timed region ----
+        dens = (16 + 1) / (2.0 * 16)               # block-causal density with 16 time patches
+        S, H, HD = 4096, 16, 32
+        qk = 2.0 * B * H * S * S * HD * dens       # flops of ONE score-shaped matmul over the visible pairs
+        # algorithmic flops per launch: fwd = QK^T + PV; dK/dV kernel = S, dP, dV, dK; the dQ kernel owes only dQ
+        # (its S / dP re-computation is overhead of the two-kernel split and is not counted as useful work)
+        alg = {"vq_search": 2.0 * n_vq * VQ_K * VQ_D, "attn_fwd": 2 * qk, "attn_bwd_dkv": 4 * qk, "attn_bwd_dq": 1 * qk}
+        names = {"vq_search": "fk::vq_search_kernel (tcgen05/TMEM/TMA nearest-codeword search)",
+                 "attn_fwd": "fk::attn_fwd_kernel (label-mask flash attention forward, mma.sync bf16)",
+                 "attn_bwd_dkv": "fk::attn_bwd_dkv_kernel (label-mask flash attention dK/dV, mma.sync bf16)",
+                 "attn_bwd_dq": "fk::attn_bwd_dq_kernel (label-mask flash attention dQ, mma.sync bf16)"}
+        # ncu --set full captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
+        traffic = {"vq_search": NCU_TRAFFIC.get("vq_search")}
+        kern = {}
+        for name, flops in alg.items():
+            if name not in ksum:
+                continue
+            n, ms, _ = ksum[name]
+            big = [1] if name == "vq_search" else None
+            avg_ms = ms / n
+            ach = flops / (avg_ms * 1e-3) / 1e12
+            kern[name] = {"kernel": names[name], "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
+                          "frac": ach / tc_peak, "traffic": traffic.get(name), "algorithmic_flops_per_launch": flops,
+                          "avg_launch_ms": avg_ms, "launches_timed": n, "ms_per_step": ms / K, "peak_source": peak_src}
+        # the roofline object is the kernel with the largest share of the step
+        roof = None
+        if kern:
+            dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+            roof = dict(kern[dom])
+            roof["share_of_step"] = roof["ms_per_step"] / (ms_total / K)
         total_trials = B * world * K
         line = {
             "metric": "trials/sec VQ+Brainformer train step", "value": total_trials / (ms_total * 1e-3), "unit": "trials/s",
@@ -334,6 +350,7 @@ def main():
             "gpu_launches": int(launches),
             "loss": final_loss,
             "roofline": roof,
+            "vq_search": kern.get("vq_search"),
             "kernels": kern,
         }
         if world == 1 and not args.no_cpu_baseline:

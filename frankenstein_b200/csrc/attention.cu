@@ -652,9 +652,10 @@ FK_API int fk_attn_backward(const void* q, const void* k, const void* v, const v
                             long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs, long long v_ts,
                             long long o_bs, long long o_ts, long long do_bs, long long do_ts, long long dq_bs, long long dq_ts,
                             long long dk_bs, long long dk_ts, long long dv_bs, long long dv_ts, const int* qid, const int* kid,
-                            const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, void* stream_) {
+                            const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, int parts, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(head_dim == kHD, "fk_attn_backward: only head_dim 32 is built");
+  FK_REQUIRE(parts > 0 && parts < 8, "fk_attn_backward: parts is a bitmask of 1 (delta), 2 (dK/dV), 4 (dQ)");
   FK_REQUIRE(q && k && v && o && d_o && lse && delta && dq && dk && dv && B > 0 && H > 0 && Sq > 0 && Sk > 0, "fk_attn_backward: bad argument");
   FK_REQUIRE((qid == nullptr) == (kid == nullptr), "fk_attn_backward: qid and kid go together");
   FK_REQUIRE(qid == nullptr || (qmin && qmax && kmin && kmax), "fk_attn_backward: label ranges missing");
@@ -669,13 +670,23 @@ FK_API int fk_attn_backward(const void* q, const void* k, const void* v, const v
   p.do_bs = do_bs; p.do_ts = do_ts; p.dq_bs = dq_bs; p.dq_ts = dq_ts; p.dk_bs = dk_bs; p.dk_ts = dk_ts; p.dv_bs = dv_bs; p.dv_ts = dv_ts;
   p.qid = qid; p.kid = kid; p.qmin = qmin; p.qmax = qmax; p.kmin = kmin; p.kmax = kmax;
   const long long nd = static_cast<long long>(B) * Sq * H;
-  attn_delta_kernel<<<static_cast<unsigned>((nd + 255) / 256), 256, 0, stream>>>(p);
-  FK_CHECK_LAUNCH();
-  attn_bwd_dkv_kernel<<<dim3((Sk + kTQ - 1) / kTQ, H, B), kAttnThreads, 0, stream>>>(p);
-  FK_CHECK_LAUNCH();
-  attn_bwd_dq_kernel<<<dim3((Sq + kTQ - 1) / kTQ, H, B), kAttnThreads, 0, stream>>>(p);
-  FK_CHECK_LAUNCH();
-  fk_count_launch(3);
+  int n = 0;
+  if (parts & 1) {
+    attn_delta_kernel<<<static_cast<unsigned>((nd + 255) / 256), 256, 0, stream>>>(p);
+    FK_CHECK_LAUNCH();
+    ++n;
+  }
+  if (parts & 2) {
+    attn_bwd_dkv_kernel<<<dim3((Sk + kTQ - 1) / kTQ, H, B), kAttnThreads, 0, stream>>>(p);
+    FK_CHECK_LAUNCH();
+    ++n;
+  }
+  if (parts & 4) {
+    attn_bwd_dq_kernel<<<dim3((Sq + kTQ - 1) / kTQ, H, B), kAttnThreads, 0, stream>>>(p);
+    FK_CHECK_LAUNCH();
+    ++n;
+  }
+  fk_count_launch(n);
   return FK_OK;
 }
 

@@ -198,7 +198,7 @@ class _AttnQKVFn(torch.autograd.Function):
         need_grad = qkv.requires_grad
         lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
         m = mask
-        with timed("attn_fwd", 4.0 * B * H * S * S * hd):
+        with timed("attn_fwd"):
           check(lib().fk_attn_forward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, S, hd,
                                     q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                                     out.stride(0), out.stride(1),
@@ -223,14 +223,15 @@ class _AttnQKVFn(torch.autograd.Function):
         dq, dk, dv = d5[:, :, 0], d5[:, :, 1], d5[:, :, 2]
         delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
         m = ctx.mask
-        with timed("attn_bwd", 14.0 * B * H * S * S * hd):
-          check(lib().fk_attn_backward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv),
-                                     B, H, S, S, hd, q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
-                                     out.stride(0), out.stride(1), d_o.stride(0), d_o.stride(1),
-                                     dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
-                                     ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0,
-                                     ptr(m.qmax) if m else 0, ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0,
-                                     float(ctx.scale), stream()), "fk_attn_backward")
+        for name, part in (("attn_delta", 1), ("attn_bwd_dkv", 2), ("attn_bwd_dq", 4)):
+            with timed(name):
+                check(lib().fk_attn_backward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk),
+                                             ptr(dv), B, H, S, S, hd, q.stride(0), q.stride(1), k.stride(0), k.stride(1),
+                                             v.stride(0), v.stride(1), out.stride(0), out.stride(1), d_o.stride(0), d_o.stride(1),
+                                             dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
+                                             ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0,
+                                             ptr(m.qmax) if m else 0, ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0,
+                                             float(ctx.scale), part, stream()), "fk_attn_backward")
         if ctx.rope is not None:
             _rope_inplace(dq, ctx.rope, True)
             _rope_inplace(dk, ctx.rope, True)

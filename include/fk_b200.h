@@ -123,13 +123,14 @@ int fk_attn_forward(const void* q, const void* k, const void* v, void* out, floa
                     int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
                     long long v_ts, long long o_bs, long long o_ts, const int* qid, const int* kid, const int* qmin,
                     const int* qmax, const int* kmin, const int* kmax, float scale, void* stream);
-/* delta: [B,H,Sq] fp32 workspace.  dq/dk/dv: bf16, same addressing scheme as q/k/v. */
+/* delta: [B,H,Sq] fp32 workspace.  dq/dk/dv: bf16, same addressing scheme as q/k/v.
+ * parts: bitmask of the kernels to launch, in this order: 1 = delta = rowsum(dO*O), 2 = dK/dV, 4 = dQ (7 = all). */
 int fk_attn_backward(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                      float* delta, void* dq, void* dk, void* dv, int B, int H, int Sq, int Sk, int head_dim,
                      long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs, long long v_ts,
                      long long o_bs, long long o_ts, long long do_bs, long long do_ts, long long dq_bs, long long dq_ts,
                      long long dk_bs, long long dk_ts, long long dv_bs, long long dv_ts, const int* qid, const int* kid,
-                     const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, void* stream);
+                     const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, int parts, void* stream);
 
 #ifdef __cplusplus
 }
