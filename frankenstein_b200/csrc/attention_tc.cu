@@ -1,0 +1,490 @@
+// Attention backward on the 5th-gen tensor cores (tcgen05.mma + TMEM + TMA), head_dim 32, label masks.
+//
+// Same math and mask rule as attention.cu (reference: F.scaled_dot_product_attention backward at
+// models/brainformer.py:168), restructured for Blackwell: every matmul is a tcgen05.mma issued by one thread,
+// score tiles live in TMEM, and each compute thread owns one resident row, so the per-row statistics never
+// need a shuffle.  Two launches of one kernel template:
+//
+//   MODE_DKV  CTA owns 128 keys (resident K, V), streams 64-query tiles (Q, dO + their transposes Qt, dOt):
+//             S^T = K Q^T, dP^T = V dO^T  (TMEM)  ->  P^T = 2^(S^T c - lse[q]),  dS^T = P^T (dP^T - delta[q])
+//             -> bf16 operands in smem  ->  dV += P^T dO,  dK += dS^T Q  (TMEM accumulators, 32 columns each)
+//   MODE_DQ   CTA owns 128 queries (resident Q, dO), streams 64-key tiles (K, V + Kt):
+//             S = Q K^T, dP = dO V^T  ->  P, dS  ->  dQ += dS K
+//
+// Pipeline per CTA (384 threads): warp 0 = TMA producer (4-stage ring of streamed tiles), warp 1 = MMA issuer
+// (score MMAs of tile j are queued before the accumulate MMAs of tile j-1), warp 2 = TMEM allocator, warp 3
+// builds the list of visible tiles, warps 4-7 / 8-11 = two compute warpgroups that alternate tiles, each with
+// its own TMEM score stage and its own P/dS smem operand buffers.  Operand layouts: [tokens][32] tiles are
+// TMA-loaded with the 64-byte swizzle (K-major, K = head dim); the transposed [32][tokens] tiles and the P/dS
+// tiles use the 128-byte swizzle (K-major, K = tokens) -- the compute threads write P/dS with that swizzle by
+// hand and publish them to the async proxy with fence.proxy.async.
+#include "common.cuh"
+#include "tma_host.cuh"
+
+namespace fk {
+
+constexpr int kRows = 128;        // resident rows per CTA (UMMA M)
+constexpr int kCols = 64;         // streamed tile (UMMA N of the score MMAs, K of the accumulate MMAs)
+constexpr int kNST = 4;           // streamed smem stages
+constexpr int kTcThreads = 384;
+constexpr int kMaxTiles = 2048;   // streamed tiles per sequence (S <= 131072)
+constexpr int MODE_DKV = 0, MODE_DQ = 1;
+
+struct TcParams {
+  const int *row_id, *col_id;                          // labels of the resident / streamed side, or null
+  const int *row_min, *row_max, *col_min, *col_max;    // per-64-token tile label ranges
+  const float *lse, *delta;                            // [B, H, Sq]
+  __nv_bfloat16 *out0, *out1;                          // DKV: dV, dK.  DQ: (unused), dQ
+  long long o0_bs, o0_ts, o1_bs, o1_ts;
+  int B, H, S_row, S_col, Sq;
+  float scale, scale_log2;
+};
+
+struct TcSmem {
+  // offsets from the 1024-aligned dynamic smem base
+  static constexpr int resA = 0;                       // 128 x 64 B
+  static constexpr int resB = 8192;
+  static constexpr int stream = 16384;                 // kNST x 16 KB: stA | stB | tA | tB (4 KB each)
+  static constexpr int pbuf = stream + kNST * 16384;   // [2 wg][P | dS] x 16 KB
+  static constexpr int stats = pbuf + 65536;           // [2 wg][lse | delta | id][64] x 4 B
+  static constexpr int tiles = stats + 2 * 3 * 64 * 4; // uint16 visible-tile list
+  static constexpr int bars = tiles + kMaxTiles * 2;
+  static constexpr int total = bars + 256;
+};
+
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void tmem_ld32_dep(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_wait2(uint32_t (&a)[32], uint32_t (&b)[32]) {
+  // wait::ld with both destination arrays as in/out operands so no use is scheduled above the wait
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                 "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]),
+                 "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
+               :: "memory");
+  asm volatile("" : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                    "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]),
+                    "+r"(b[16]), "+r"(b[17]), "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]),
+                    "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
+               :: "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_constant__ CUtensorMap tm_resB,
+                   const __grid_constant__ CUtensorMap tm_stA, const __grid_constant__ CUtensorMap tm_stB,
+                   const __grid_constant__ CUtensorMap tm_tA, const __grid_constant__ CUtensorMap tm_tB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);
+  uint64_t* res_full = bars;               // [1]
+  uint64_t* st_full = bars + 1;            // [kNST]
+  uint64_t* st_empty = bars + 1 + kNST;    // [kNST]
+  uint64_t* sdp_full = bars + 1 + 2 * kNST;   // [2]
+  uint64_t* tmem_free = sdp_full + 2;      // [2]
+  uint64_t* p_ready = sdp_full + 4;        // [2]
+  uint64_t* p_free = sdp_full + 6;         // [2]
+  uint64_t* acc_full = sdp_full + 8;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 9);
+  int* n_tiles_slot = reinterpret_cast<int*>(sdp_full + 9) + 1;
+  uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + TcSmem::tiles);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int r0 = rt * kRows;
+  const bool masked = p.row_id != nullptr;
+  const int n_col_tiles = (p.S_col + kCols - 1) / kCols;
+  const int n_row_tiles64 = (p.S_row + 63) / 64;
+
+  // label range of the resident rows (two 64-token range entries)
+  int row_lo = 0, row_hi = 0;
+  if (masked) {
+    const int i0 = rt * 2, i1 = min(rt * 2 + 1, n_row_tiles64 - 1);
+    row_lo = min(p.row_min[b * n_row_tiles64 + i0], p.row_min[b * n_row_tiles64 + i1]);
+    row_hi = max(p.row_max[b * n_row_tiles64 + i0], p.row_max[b * n_row_tiles64 + i1]);
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_resA); tma_prefetch_desc(&tm_resB); tma_prefetch_desc(&tm_stA);
+    tma_prefetch_desc(&tm_stB); tma_prefetch_desc(&tm_tB);
+    if (MODE == MODE_DKV) tma_prefetch_desc(&tm_tA);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(res_full, 1);
+    for (int i = 0; i < kNST; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&tmem_free[i], 4);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&p_free[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp == 3) {
+    // visible streamed tiles, in order (DKV: q tiles with qmax >= kmin(rows); DQ: k tiles with kmin <= qmax(rows))
+    int cnt = 0;
+    for (int base = 0; base < n_col_tiles; base += 32) {
+      const int t = base + lane;
+      bool vis = t < n_col_tiles;
+      if (vis && masked) {
+        vis = (MODE == MODE_DKV) ? (p.col_max[b * n_col_tiles + t] >= row_lo) : (p.col_min[b * n_col_tiles + t] <= row_hi);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, vis);
+      if (vis) tile_list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(t);
+      cnt += __popc(m);
+    }
+    if (lane == 0) *n_tiles_slot = cnt;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int T = *n_tiles_slot;
+
+  constexpr uint32_t kStageBytes = (MODE == MODE_DKV) ? 16384u : 12288u;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(res_full, 16384);
+      tma_load_4d(smem + TcSmem::resA, &tm_resA, res_full, 0, h, r0, b);
+      tma_load_4d(smem + TcSmem::resB, &tm_resB, res_full, 0, h, r0, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        const int t = tile_list[j];
+        uint8_t* st = smem + TcSmem::stream + stage * 16384;
+        mbar_wait(&st_empty[stage], phase ^ 1);
+        mbar_expect_tx(&st_full[stage], kStageBytes);
+        tma_load_4d(st, &tm_stA, &st_full[stage], 0, h, t * kCols, b);
+        tma_load_4d(st + 4096, &tm_stB, &st_full[stage], 0, h, t * kCols, b);
+        if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+        tma_load_2d(st + 12288, &tm_tB, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+        if (++stage == kNST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_score = umma_idesc_bf16(kRows, kCols);
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(kRows, 32);
+      const uint32_t resA = smem_u32(smem + TcSmem::resA), resB = smem_u32(smem + TcSmem::resB);
+      const uint32_t stream = smem_u32(smem + TcSmem::stream), pbuf = smem_u32(smem + TcSmem::pbuf);
+      auto acc_mmas = [&](int i) {
+        const int g = i & 1, n = i >> 1, stage = i % kNST;
+        mbar_wait(&p_ready[g], n & 1);
+        tc_fence_after();
+        const uint32_t st = stream + stage * 16384;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (MODE == MODE_DKV)
+            umma_bf16(tmem_base + 256, umma_desc_sw128(pbuf + g * 32768 + kk * 32), umma_desc_sw128(st + 8192 + kk * 32),
+                      idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16(tmem_base + 288, umma_desc_sw128(pbuf + g * 32768 + 16384 + kk * 32),
+                    umma_desc_sw128(st + 12288 + kk * 32), idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&p_free[g]);
+        umma_commit(&st_empty[stage]);
+      };
+      mbar_wait(res_full, 0);
+      tc_fence_after();
+      for (int j = 0; j < T; ++j) {
+        const int g = j & 1, n = j >> 1, stage = j % kNST;
+        mbar_wait(&st_full[stage], (j / kNST) & 1);
+        mbar_wait(&tmem_free[g], (n & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t st = stream + stage * 16384;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          umma_bf16(tmem_base + g * 128, umma_desc_sw64(resA + kk * 32), umma_desc_sw64(st + kk * 32), idesc_score, kk);
+          umma_bf16(tmem_base + g * 128 + 64, umma_desc_sw64(resB + kk * 32), umma_desc_sw64(st + 4096 + kk * 32), idesc_score, kk);
+        }
+        umma_commit(&sdp_full[g]);
+        if (j >= 1) acc_mmas(j - 1);
+      }
+      if (T >= 1) acc_mmas(T - 1);
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    // ================================ compute warpgroups ================================
+    const int g = (warp - 4) >> 2;               // warpgroup = tile parity
+    const int q4 = warp & 3;                     // TMEM lane quarter
+    const int r = q4 * 32 + lane;                // resident row owned by this thread
+    const int tid = (warp - 4 - g * 4) * 32 + lane;
+    const int row = r0 + r;
+    const bool row_ok = row < p.S_row;
+    float* s_lse = reinterpret_cast<float*>(smem + TcSmem::stats) + g * 192;
+    float* s_delta = s_lse + 64;
+    int* s_id = reinterpret_cast<int*>(s_lse + 128);
+    const float* lse_g = p.lse + (static_cast<long long>(b) * p.H + h) * p.Sq;
+    const float* delta_g = p.delta + (static_cast<long long>(b) * p.H + h) * p.Sq;
+    const int my_id = masked ? (row_ok ? p.row_id[static_cast<long long>(b) * p.S_row + row]
+                                       : (MODE == MODE_DKV ? 0x7fffffff : -0x7fffffff))
+                             : 0;
+    float my_lse = INFINITY, my_delta = 0.f;     // DQ: per-row statistics
+    if (MODE == MODE_DQ && row_ok) { my_lse = lse_g[row]; my_delta = delta_g[row]; }
+    uint8_t* Pb = smem + TcSmem::pbuf + g * 32768;
+    uint8_t* Sb = Pb + 16384;
+
+    // column statistics of a streamed tile, fetched one own-tile ahead
+    float pre_f = 0.f;
+    int pre_i = 0;
+    auto prefetch = [&](int j) {
+      if (j >= T) return;
+      const int c = tile_list[j] * kCols + (tid & 63);
+      const bool ok = c < p.S_col;
+      if (MODE == MODE_DKV) {
+        if (tid < 64) {
+          pre_f = ok ? lse_g[c] : INFINITY;
+          pre_i = masked ? (ok ? p.col_id[static_cast<long long>(b) * p.S_col + c] : -0x7fffffff) : 0;
+        } else {
+          pre_f = ok ? delta_g[c] : 0.f;
+        }
+      } else if (tid < 64) {
+        pre_i = ok ? (masked ? p.col_id[static_cast<long long>(b) * p.S_col + c] : 0) : 0x7fffffff;
+      }
+    };
+    prefetch(g);
+    for (int j = g; j < T; j += 2) {
+      const int n = j >> 1, t = tile_list[j];
+      named_bar_sync(1 + g, 128);                        // the previous tile's statistics are no longer read
+      if (MODE == MODE_DKV) {
+        if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else { s_delta[tid - 64] = pre_f; }
+      } else if (tid < 64) {
+        s_id[tid] = pre_i;
+      }
+      named_bar_sync(1 + g, 128);
+      prefetch(j + 2);
+      bool need_mask;
+      if (MODE == MODE_DKV) need_mask = masked && (row_hi > p.col_min[b * n_col_tiles + t]);
+      else need_mask = (masked && (p.col_max[b * n_col_tiles + t] > row_lo)) || (t * kCols + kCols > p.S_col);
+      mbar_wait(&sdp_full[g], n & 1);
+      tc_fence_after();
+      mbar_wait(&p_free[g], (n & 1) ^ 1);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + g * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(taddr + c * 32, sv);
+        tmem_ld32(taddr + 64 + c * 32, dv);
+        tmem_wait2(sv, dv);
+        if (c == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_free[g]);
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          uint32_t pw[4], dw[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            float pv[2], ds[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = c * 32 + g8 * 8 + e2 * 2 + e;
+              float s = __uint_as_float(sv[g8 * 8 + e2 * 2 + e]);
+              const float d = __uint_as_float(dv[g8 * 8 + e2 * 2 + e]);
+              float lse, dl;
+              if (MODE == MODE_DKV) { lse = s_lse[col]; dl = s_delta[col]; } else { lse = my_lse; dl = my_delta; }
+              if (need_mask) {
+                const int cid = s_id[col];
+                const bool hide = (MODE == MODE_DKV) ? (my_id > cid) : (cid > my_id);
+                if (hide) s = -INFINITY;
+              }
+              pv[e] = fast_ex2(fmaf(s, p.scale_log2, -lse));
+              ds[e] = pv[e] * (d - dl);
+            }
+            pw[e2] = pack2(pv[0], pv[1]);
+            dw[e2] = pack2(ds[0], ds[1]);
+          }
+          const int chunk = c * 4 + g8;                         // 16-byte chunk of this row (8 columns)
+          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+          if (MODE == MODE_DKV) *reinterpret_cast<uint4*>(Pb + off) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *reinterpret_cast<uint4*>(Sb + off) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        }
+      }
+      fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+    }
+    // ---- epilogue: accumulators -> bf16 -> global ----
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool writes = (MODE == MODE_DKV) || (g == 1);     // warp-uniform
+    if (writes) {
+      const int which = (MODE == MODE_DKV) ? g : 1;      // wg0 -> acc0 (dV), wg1 -> acc1 (dK / dQ)
+      uint32_t acc[32];
+      if (T > 0) {                                        // uniform: the whole warp executes the aligned TMEM load
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + 256 + which * 32, acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+                       "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]), "+r"(acc[14]), "+r"(acc[15]),
+                       "+r"(acc[16]), "+r"(acc[17]), "+r"(acc[18]), "+r"(acc[19]), "+r"(acc[20]), "+r"(acc[21]), "+r"(acc[22]), "+r"(acc[23]),
+                       "+r"(acc[24]), "+r"(acc[25]), "+r"(acc[26]), "+r"(acc[27]), "+r"(acc[28]), "+r"(acc[29]), "+r"(acc[30]), "+r"(acc[31])
+                     :: "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0u;
+      }
+      if (row_ok) {
+        const float sc = (which == 1) ? p.scale : 1.f;
+        __nv_bfloat16* dst = (which == 0 ? p.out0 + b * p.o0_bs + static_cast<long long>(row) * p.o0_ts
+                                         : p.out1 + b * p.o1_bs + static_cast<long long>(row) * p.o1_ts) + h * 32;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            w[e] = pack2(__uint_as_float(acc[c4 * 8 + e * 2]) * sc, __uint_as_float(acc[c4 * 8 + e * 2 + 1]) * sc);
+          *reinterpret_cast<uint4*>(dst + c4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// [B][S][H][32] (strided) -> [B][H][32][Sp] (zero padded beyond S): the K-major operand for contractions over tokens
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_transpose_kernel(const __nv_bfloat16* __restrict__ x, long long bs, long long ts, int S, int H, int Sp,
+                      __nv_bfloat16* __restrict__ xt) {
+  __shared__ __nv_bfloat16 tile[64][34];
+  const int t0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  // load 64 tokens x 32 dims: 4 threads per token, 16 bytes each
+  {
+    const int tok = threadIdx.x >> 2, c = threadIdx.x & 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (t0 + tok < S) v = *reinterpret_cast<const uint4*>(x + b * bs + static_cast<long long>(t0 + tok) * ts + h * 32 + c * 8);
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[tok][c * 8 + i] = e[i];
+  }
+  __syncthreads();
+  // store 32 rows (d) x 64 tokens: 8 threads per row, 8 tokens (16 bytes) each
+  {
+    const int d = threadIdx.x >> 3, c = threadIdx.x & 7;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 pr;
+      pr.x = tile[c * 8 + 2 * i][d];
+      pr.y = tile[c * 8 + 2 * i + 1][d];
+      w[i] = *reinterpret_cast<uint32_t*>(&pr);
+    }
+    if (t0 + c * 8 < Sp)
+      *reinterpret_cast<uint4*>(xt + ((static_cast<long long>(b) * H + h) * 32 + d) * Sp + t0 + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+}  // namespace fk
+
+using namespace fk;
+
+#define FK_API extern "C" __attribute__((visibility("default")))
+
+FK_API int fk_attn_transpose(const void* x, long long bs, long long ts, int B, int S, int H, int head_dim, void* xt, int Sp,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(head_dim == 32, "fk_attn_transpose: only head_dim 32 is built");
+  FK_REQUIRE(x && xt && B > 0 && S > 0 && H > 0 && Sp >= S && Sp % 8 == 0, "fk_attn_transpose: bad argument (Sp % 8 == 0)");
+  FK_REQUIRE(ts % 8 == 0 && bs % 8 == 0, "fk_attn_transpose: strides must keep 16-byte alignment");
+  attn_transpose_kernel<<<dim3((Sp + 63) / 64, H, B), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), bs, ts, S, H, Sp,
+                                                                        static_cast<__nv_bfloat16*>(xt));
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+// parts: 2 = dK/dV (needs qt, dot), 4 = dQ (needs kt).  delta must already hold rowsum(dO * O) (fk_attn_backward parts=1).
+FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
+                               const void* dot, int Sp, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+                               int B, int H, int S, int head_dim, long long q_bs, long long q_ts, long long k_bs,
+                               long long k_ts, long long v_bs, long long v_ts, long long do_bs, long long do_ts,
+                               long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
+                               long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
+                               const int* kmin, const int* kmax, float scale, int parts, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(head_dim == 32, "fk_attn_backward_tc: only head_dim 32 is built");
+  FK_REQUIRE(q && k && v && d_o && lse && delta && B > 0 && H > 0 && S > 0, "fk_attn_backward_tc: bad argument");
+  FK_REQUIRE((parts & ~6) == 0 && parts != 0, "fk_attn_backward_tc: parts is a bitmask of 2 (dK/dV) and 4 (dQ)");
+  FK_REQUIRE((qid == nullptr) == (kid == nullptr), "fk_attn_backward_tc: qid and kid go together");
+  FK_REQUIRE(qid == nullptr || (qmin && qmax && kmin && kmax), "fk_attn_backward_tc: label ranges missing");
+  FK_REQUIRE((S + kCols - 1) / kCols <= kMaxTiles, "fk_attn_backward_tc: sequence too long");
+  FK_REQUIRE(Sp >= S && Sp % 8 == 0, "fk_attn_backward_tc: Sp must be >= S and a multiple of 8");
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess) {
+      fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
+      return FK_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  CUtensorMap mQ128, mDO128, mK128, mV128, mQ64, mDO64, mK64, mV64, mQt, mKt, mDOt;
+  int rc = 0;
+  rc |= make_tmap_heads_sw64(&mQ128, q, B, S, H, q_bs, q_ts, kRows);
+  rc |= make_tmap_heads_sw64(&mDO128, d_o, B, S, H, do_bs, do_ts, kRows);
+  rc |= make_tmap_heads_sw64(&mK128, k, B, S, H, k_bs, k_ts, kRows);
+  rc |= make_tmap_heads_sw64(&mV128, v, B, S, H, v_bs, v_ts, kRows);
+  rc |= make_tmap_heads_sw64(&mQ64, q, B, S, H, q_bs, q_ts, kCols);
+  rc |= make_tmap_heads_sw64(&mDO64, d_o, B, S, H, do_bs, do_ts, kCols);
+  rc |= make_tmap_heads_sw64(&mK64, k, B, S, H, k_bs, k_ts, kCols);
+  rc |= make_tmap_heads_sw64(&mV64, v, B, S, H, v_bs, v_ts, kCols);
+  const uint64_t trows = static_cast<uint64_t>(B) * H * 32;
+  if (parts & 2) {
+    FK_REQUIRE(qt && dot && dk && dv, "fk_attn_backward_tc: dK/dV needs qt, dot, dk, dv");
+    rc |= make_tmap_bf16_sw128(&mQt, qt, trows, static_cast<uint64_t>(Sp), 32);
+    rc |= make_tmap_bf16_sw128(&mDOt, dot, trows, static_cast<uint64_t>(Sp), 32);
+  }
+  if (parts & 4) {
+    FK_REQUIRE(kt && dq, "fk_attn_backward_tc: dQ needs kt, dq");
+    rc |= make_tmap_bf16_sw128(&mKt, kt, trows, static_cast<uint64_t>(Sp), 32);
+  }
+  if (rc != 0) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
+  const dim3 grid((S + kRows - 1) / kRows, H, B);
+  int n = 0;
+  if (parts & 2) {
+    TcParams p = {};
+    p.row_id = kid; p.col_id = qid; p.row_min = kmin; p.row_max = kmax; p.col_min = qmin; p.col_max = qmax;
+    p.lse = lse; p.delta = delta;
+    p.out0 = static_cast<__nv_bfloat16*>(dv); p.o0_bs = dv_bs; p.o0_ts = dv_ts;
+    p.out1 = static_cast<__nv_bfloat16*>(dk); p.o1_bs = dk_bs; p.o1_ts = dk_ts;
+    p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+    attn_bwd_tc_kernel<MODE_DKV><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
+    FK_CHECK_LAUNCH();
+    ++n;
+  }
+  if (parts & 4) {
+    TcParams p = {};
+    p.row_id = qid; p.col_id = kid; p.row_min = qmin; p.row_max = qmax; p.col_min = kmin; p.col_max = kmax;
+    p.lse = lse; p.delta = delta;
+    p.out0 = nullptr; p.out1 = static_cast<__nv_bfloat16*>(dq); p.o1_bs = dq_bs; p.o1_ts = dq_ts;
+    p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+    attn_bwd_tc_kernel<MODE_DQ><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
+    FK_CHECK_LAUNCH();
+    ++n;
+  }
+  fk_count_launch(n);
+  return FK_OK;
+}

@@ -136,6 +136,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------
@@ -180,6 +187,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;           // SBO = 1024 B   [32,46)
   d |= static_cast<uint64_t>(1) << 46;                   // version = 1    [46,48)
   d |= static_cast<uint64_t>(2) << 61;                   // SWIZZLE_128B   [61,64)
+  return d;
+}
+
+// Same for rows of 32 bf16 (64 B) written by TMA with CU_TENSOR_MAP_SWIZZLE_64B: 8-row groups are 512 B apart,
+// layout type 4 = SWIZZLE_64B; the tile must be 512-byte aligned; a K step of 16 elements adds 32 B.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
   return d;
 }
 

@@ -25,6 +25,7 @@
 // Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 =
 // TMEM allocator, warps 4-19 = epilogue (TMEM lane quarter x accumulator half x column half).
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace fk {
 
@@ -304,36 +305,6 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* ptr = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  return fn;
-}
-
-// bf16 row-major [rows, cols] matrix, box = 64 columns x box_rows rows, 128-byte swizzle.
-int make_tmap_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return FK_ERR_DRIVER;
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? FK_OK : FK_ERR_DRIVER;
-}
-
 static int sm_count() {
   static int n = 0;
   if (!n) {

@@ -14,6 +14,11 @@ from ._lib import FkError, check, lib, ptr, require_cuda, require_device, stream
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
+import os
+
+# attention backward implementation: "tc" = tcgen05/TMEM/TMA kernels (attention_tc.cu), "legacy" = mma.sync kernels
+ATTN_BWD_IMPL = os.environ.get("FK_ATTN_BWD", "tc")
+
 
 # ------------------------------------------------------------------------------------------------
 # LayerNorm / RMSNorm
@@ -223,15 +228,40 @@ class _AttnQKVFn(torch.autograd.Function):
         dq, dk, dv = d5[:, :, 0], d5[:, :, 1], d5[:, :, 2]
         delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
         m = ctx.mask
-        for name, part in (("attn_delta", 1), ("attn_bwd_dkv", 2), ("attn_bwd_dq", 4)):
+        common = (ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0, ptr(m.qmax) if m else 0,
+                  ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0, float(ctx.scale))
+
+        def legacy(name, part):
             with timed(name):
                 check(lib().fk_attn_backward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk),
                                              ptr(dv), B, H, S, S, hd, q.stride(0), q.stride(1), k.stride(0), k.stride(1),
                                              v.stride(0), v.stride(1), out.stride(0), out.stride(1), d_o.stride(0), d_o.stride(1),
                                              dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
-                                             ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0,
-                                             ptr(m.qmax) if m else 0, ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0,
-                                             float(ctx.scale), part, stream()), "fk_attn_backward")
+                                             *common, part, stream()), "fk_attn_backward")
+
+        legacy("attn_delta", 1)
+        if ATTN_BWD_IMPL == "legacy":
+            legacy("attn_bwd_dkv", 2)
+            legacy("attn_bwd_dq", 4)
+        else:
+            # tcgen05 path: K-major (token-contiguous) copies of q, k, dO for the contractions over tokens
+            Sp = (S + 7) // 8 * 8
+            d4 = d_o.view(B, S, H, hd)
+            tr = {}
+            with timed("attn_transpose"):
+                for name, src in (("q", q), ("k", k), ("do", d4)):
+                    t = torch.empty(B, H, hd, Sp, device=qkv.device, dtype=torch.bfloat16)
+                    check(lib().fk_attn_transpose(ptr(src), src.stride(0), src.stride(1), B, S, H, hd, ptr(t), Sp, stream()),
+                          "fk_attn_transpose")
+                    tr[name] = t
+            for name, part in (("attn_bwd_dkv", 2), ("attn_bwd_dq", 4)):
+                with timed(name):
+                    check(lib().fk_attn_backward_tc(ptr(q), ptr(k), ptr(v), ptr(d4), ptr(tr["q"]), ptr(tr["k"]), ptr(tr["do"]), Sp,
+                                                    ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv), B, H, S, hd,
+                                                    q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                                    d4.stride(0), d4.stride(1), dq.stride(0), dq.stride(1), dk.stride(0),
+                                                    dk.stride(1), dv.stride(0), dv.stride(1), *common, part, stream()),
+                          "fk_attn_backward_tc")
         if ctx.rope is not None:
             _rope_inplace(dq, ctx.rope, True)
             _rope_inplace(dk, ctx.rope, True)

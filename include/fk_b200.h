@@ -132,6 +132,20 @@ int fk_attn_backward(const void* q, const void* k, const void* v, const void* o,
                      long long dk_bs, long long dk_ts, long long dv_bs, long long dv_ts, const int* qid, const int* kid,
                      const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, int parts, void* stream);
 
+/* tcgen05 / TMEM / TMA version of the attention backward (attention_tc.cu).  fk_attn_transpose makes the
+ * [B][H][32][Sp] copies (zero padded, Sp % 8 == 0) that serve as K-major operands for contractions over tokens:
+ * qt, dot for dK/dV (parts & 2), kt for dQ (parts & 4).  delta must already hold rowsum(dO*O)
+ * (fk_attn_backward with parts = 1).  Same labels / ranges / strides conventions as fk_attn_backward; Sq == Sk == S. */
+int fk_attn_transpose(const void* x, long long bs, long long ts, int B, int S, int H, int head_dim, void* xt, int Sp,
+                      void* stream);
+int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
+                        const void* dot, int Sp, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+                        int B, int H, int S, int head_dim, long long q_bs, long long q_ts, long long k_bs,
+                        long long k_ts, long long v_bs, long long v_ts, long long do_bs, long long do_ts,
+                        long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
+                        long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
+                        const int* kmin, const int* kmax, float scale, int parts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,10 +38,12 @@ def _labels(kind, B, S, dev, g):
     raise ValueError(kind)
 
 
+@pytest.mark.parametrize("impl", ["tc", "legacy"])
 @pytest.mark.parametrize("kind", ["none", "block64", "block48", "gathered", "padding"])
 @pytest.mark.parametrize("B,S,H", [(2, 512, 4), (1, 300, 2), (3, 70, 1)])
-def test_attention_fwd_bwd(kind, B, S, H):
+def test_attention_fwd_bwd(kind, B, S, H, impl, monkeypatch):
     from frankenstein_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_BWD_IMPL", impl)
     g = torch.Generator().manual_seed(B * 1000 + S)
     dev = torch.device("cuda")
     qkv = (torch.randn(B, S, 3 * H * 32, generator=g) * 1.5).to(dev).to(torch.bfloat16)
