@@ -12,12 +12,14 @@
 //             S = Q K^T, dP = dO V^T  ->  P, dS  ->  dQ += dS K
 //
 // Pipeline per CTA (384 threads): warp 0 = TMA producer (4-stage ring of streamed tiles), warp 1 = MMA issuer
-// (score MMAs of tile j are queued before the accumulate MMAs of tile j-1), warp 2 = TMEM allocator, warp 3
-// builds the list of visible tiles, warps 4-7 / 8-11 = two compute warpgroups that alternate tiles, each with
-// its own TMEM score stage and its own P/dS smem operand buffers.  Operand layouts: [tokens][32] tiles are
-// TMA-loaded with the 64-byte swizzle (K-major, K = head dim); the transposed [32][tokens] tiles and the P/dS
-// tiles use the 128-byte swizzle (K-major, K = tokens) -- the compute threads write P/dS with that swizzle by
-// hand and publish them to the async proxy with fence.proxy.async.
+// of the score products, warp 2 = TMEM allocator, warp 3 = builds the list of visible tiles, then issues the
+// accumulate MMAs, warps 4-7 / 8-11 = two compute warpgroups that alternate tiles, each with
+// tiles round-robin over three TMEM score stages.  P / dS never touch shared memory: a compute thread packs its
+// row to bf16 and writes it back into the stage's own TMEM columns (tcgen05.st), and the accumulate MMAs read
+// that as their A operand straight from TMEM (TS mode) -- the smem data pipe, which bounds an SS-mode version of
+// this kernel, only carries the streamed operands.  Operand layouts: [tokens][32] tiles are TMA-loaded with the
+// 64-byte swizzle (K-major, K = head dim); the transposed [32][tokens] tiles use the 128-byte swizzle (K-major,
+// K = tokens).
 #include "common.cuh"
 #include "tma_host.cuh"
 
@@ -26,8 +28,11 @@ namespace fk {
 constexpr int kRows = 128;        // resident rows per CTA (UMMA M)
 constexpr int kCols = 64;         // streamed tile (UMMA N of the score MMAs, K of the accumulate MMAs)
 constexpr int kNST = 4;           // streamed smem stages
+constexpr int kNP = 3;            // TMEM operand buffers for P | dS (bf16 pairs, 64 columns each)
+// TMEM map (512 columns): score stage of warpgroup g at g*128 (S 64 | dP 64); operand buffer b at 256 + b*64
+// (P 32 | dS 32); accumulators at 448 (dV) and 480 (dK / dQ).
 constexpr int kTcThreads = 384;
-constexpr int kMaxTiles = 2048;   // streamed tiles per sequence (S <= 131072)
+constexpr int kMaxTiles = 2048;   // streamed tiles per sequence (S <= 131072); entries carry a flag in bit 15
 constexpr int MODE_DKV = 0, MODE_DQ = 1;
 
 struct TcParams {
@@ -45,8 +50,7 @@ struct TcSmem {
   static constexpr int resA = 0;                       // 128 x 64 B
   static constexpr int resB = 8192;
   static constexpr int stream = 16384;                 // kNST x 16 KB: stA | stB | tA | tB (4 KB each)
-  static constexpr int pbuf = stream + kNST * 16384;   // [2 wg][P | dS] x 16 KB
-  static constexpr int stats = pbuf + 65536;           // [2 wg][lse | delta | id][64] x 4 B
+  static constexpr int stats = stream + kNST * 16384;  // [2 wg][lse | delta | id][64] x 4 B           // [2 wg][lse | delta | id][64] x 4 B
   static constexpr int tiles = stats + 2 * 3 * 64 * 4; // uint16 visible-tile list
   static constexpr int bars = tiles + kMaxTiles * 2;
   static constexpr int total = bars + 256;
@@ -88,13 +92,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   uint64_t* res_full = bars;               // [1]
   uint64_t* st_full = bars + 1;            // [kNST]
   uint64_t* st_empty = bars + 1 + kNST;    // [kNST]
-  uint64_t* sdp_full = bars + 1 + 2 * kNST;   // [2]
-  uint64_t* tmem_free = sdp_full + 2;      // [2]
-  uint64_t* p_ready = sdp_full + 4;        // [2]
-  uint64_t* p_free = sdp_full + 6;         // [2]
-  uint64_t* acc_full = sdp_full + 8;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 9);
-  int* n_tiles_slot = reinterpret_cast<int*>(sdp_full + 9) + 1;
+  uint64_t* sdp_full = bars + 1 + 2 * kNST;   // [2]    score stage of warpgroup g written by the tensor core
+  uint64_t* sdp_free = sdp_full + 2;       // [2]    ... read out into registers (4 warps arrive)
+  uint64_t* p_ready = sdp_free + 2;        // [kNP]  P / dS operand buffer written (4 warps arrive)
+  uint64_t* pbuf_free = p_ready + kNP;     // [kNP]  accumulate MMAs that read the buffer have retired
+  uint64_t* acc_full = pbuf_free + kNP;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  int* n_tiles_slot = reinterpret_cast<int*>(acc_full + 1) + 1;
   uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + TcSmem::tiles);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,9 +126,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     for (int i = 0; i < kNST; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&tmem_free[i], 4);
+      mbar_init(&sdp_free[i], 4);
+    }
+    for (int i = 0; i < kNP; ++i) {
       mbar_init(&p_ready[i], 4);
-      mbar_init(&p_free[i], 1);
+      mbar_init(&pbuf_free[i], 1);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -134,16 +140,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     tmem_relinquish();
   }
   if (warp == 3) {
-    // visible streamed tiles, in order (DKV: q tiles with qmax >= kmin(rows); DQ: k tiles with kmin <= qmax(rows))
+    // visible streamed tiles, in order (DKV: q tiles with qmax >= kmin(rows); DQ: k tiles with kmin <= qmax(rows)).
+    // bit 15 of an entry = the tile needs the per-element label compare (it straddles a label boundary, or it is
+    // the ragged tail of the key axis), so the compute warps never touch the range arrays in global memory.
     int cnt = 0;
     for (int base = 0; base < n_col_tiles; base += 32) {
       const int t = base + lane;
-      bool vis = t < n_col_tiles;
-      if (vis && masked) {
-        vis = (MODE == MODE_DKV) ? (p.col_max[b * n_col_tiles + t] >= row_lo) : (p.col_min[b * n_col_tiles + t] <= row_hi);
+      bool vis = t < n_col_tiles, nm = false;
+      if (vis) {
+        int cmin = 0, cmax = 0;
+        if (masked) { cmin = p.col_min[b * n_col_tiles + t]; cmax = p.col_max[b * n_col_tiles + t]; }
+        if (MODE == MODE_DKV) {
+          vis = !masked || cmax >= row_lo;
+          nm = masked && (row_hi > cmin);
+        } else {
+          vis = !masked || cmin <= row_hi;
+          nm = (masked && (cmax > row_lo)) || (t * kCols + kCols > p.S_col);
+        }
       }
       const unsigned m = __ballot_sync(0xffffffffu, vis);
-      if (vis) tile_list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(t);
+      if (vis) tile_list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(t | (nm ? 0x8000 : 0));
       cnt += __popc(m);
     }
     if (lane == 0) *n_tiles_slot = cnt;
@@ -165,7 +181,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < T; ++j) {
-        const int t = tile_list[j];
+        const int t = tile_list[j] & 0x7fff;
         uint8_t* st = smem + TcSmem::stream + stage * 16384;
         mbar_wait(&st_empty[stage], phase ^ 1);
         mbar_expect_tx(&st_full[stage], kStageBytes);
@@ -177,45 +193,49 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+    // ================================ score-MMA issuer ================================
+    // (measured on B200: one thread sustains one tcgen05.mma per ~97 cycles and the tensor core accepts one per
+    //  ~60 cycles whatever N <= 128 is -- scripts/microbench/umma_rate.cu -- so the score MMAs and the accumulate
+    //  MMAs are issued by two different threads.)
     if (lane == 0) {
       constexpr uint32_t idesc_score = umma_idesc_bf16(kRows, kCols);
-      constexpr uint32_t idesc_acc = umma_idesc_bf16(kRows, 32);
-      const uint32_t resA = smem_u32(smem + TcSmem::resA), resB = smem_u32(smem + TcSmem::resB);
-      const uint32_t stream = smem_u32(smem + TcSmem::stream), pbuf = smem_u32(smem + TcSmem::pbuf);
-      auto acc_mmas = [&](int i) {
-        const int g = i & 1, n = i >> 1, stage = i % kNST;
-        mbar_wait(&p_ready[g], n & 1);
-        tc_fence_after();
-        const uint32_t st = stream + stage * 16384;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if (MODE == MODE_DKV)
-            umma_bf16(tmem_base + 256, umma_desc_sw128(pbuf + g * 32768 + kk * 32), umma_desc_sw128(st + 8192 + kk * 32),
-                      idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
-          umma_bf16(tmem_base + 288, umma_desc_sw128(pbuf + g * 32768 + 16384 + kk * 32),
-                    umma_desc_sw128(st + 12288 + kk * 32), idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit(&p_free[g]);
-        umma_commit(&st_empty[stage]);
-      };
+      const uint64_t dA = umma_desc_sw64(smem_u32(smem + TcSmem::resA)), dB = umma_desc_sw64(smem_u32(smem + TcSmem::resB));
+      const uint32_t stream = smem_u32(smem + TcSmem::stream);
       mbar_wait(res_full, 0);
       tc_fence_after();
-      for (int j = 0; j < T; ++j) {
-        const int g = j & 1, n = j >> 1, stage = j % kNST;
-        mbar_wait(&st_full[stage], (j / kNST) & 1);
-        mbar_wait(&tmem_free[g], (n & 1) ^ 1);
+      for (int js = 0; js < T; ++js) {
+        const int stage = js % kNST, g = js & 1;
+        mbar_wait(&st_full[stage], (js / kNST) & 1);
+        mbar_wait(&sdp_free[g], ((js >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t st = stream + stage * 16384;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          umma_bf16(tmem_base + g * 128, umma_desc_sw64(resA + kk * 32), umma_desc_sw64(st + kk * 32), idesc_score, kk);
-          umma_bf16(tmem_base + g * 128 + 64, umma_desc_sw64(resB + kk * 32), umma_desc_sw64(st + 4096 + kk * 32), idesc_score, kk);
-        }
+        const uint64_t dS = umma_desc_sw64(stream + stage * 16384), dD = umma_desc_sw64(stream + stage * 16384 + 4096);
+        // a K step of 16 bf16 = 32 bytes = +2 in the descriptor's (address >> 4) field
+        umma_bf16(tmem_base + g * 128, dA, dS, idesc_score, 0u);
+        umma_bf16(tmem_base + g * 128, dA + 2, dS + 2, idesc_score, 1u);
+        umma_bf16(tmem_base + g * 128 + 64, dB, dD, idesc_score, 0u);
+        umma_bf16(tmem_base + g * 128 + 64, dB + 2, dD + 2, idesc_score, 1u);
         umma_commit(&sdp_full[g]);
-        if (j >= 1) acc_mmas(j - 1);
       }
-      if (T >= 1) acc_mmas(T - 1);
+    }
+  } else if (warp == 3) {
+    // ================================ accumulate-MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(kRows, 32);
+      const uint32_t stream = smem_u32(smem + TcSmem::stream);
+      for (int ia = 0; ia < T; ++ia) {
+        const int stage = ia % kNST, pb = ia % kNP;
+        mbar_wait(&p_ready[pb], (ia / kNP) & 1);
+        tc_fence_after();
+        const uint64_t dTA = umma_desc_sw128(stream + stage * 16384 + 8192), dTB = umma_desc_sw128(stream + stage * 16384 + 12288);
+        const uint32_t ta = tmem_base + 256 + pb * 64;       // P at +0..31, dS at +32..63 (bf16 pairs)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (MODE == MODE_DKV) umma_bf16_ts(tmem_base + 448, ta + kk * 8, dTA + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts(tmem_base + 480, ta + 32 + kk * 8, dTB + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&pbuf_free[pb]);
+        umma_commit(&st_empty[stage]);
+      }
       umma_commit(acc_full);
     }
   } else if (warp >= 4) {
@@ -236,15 +256,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
                              : 0;
     float my_lse = INFINITY, my_delta = 0.f;     // DQ: per-row statistics
     if (MODE == MODE_DQ && row_ok) { my_lse = lse_g[row]; my_delta = delta_g[row]; }
-    uint8_t* Pb = smem + TcSmem::pbuf + g * 32768;
-    uint8_t* Sb = Pb + 16384;
 
     // column statistics of a streamed tile, fetched one own-tile ahead
     float pre_f = 0.f;
     int pre_i = 0;
     auto prefetch = [&](int j) {
       if (j >= T) return;
-      const int c = tile_list[j] * kCols + (tid & 63);
+      const int c = (tile_list[j] & 0x7fff) * kCols + (tid & 63);
       const bool ok = c < p.S_col;
       if (MODE == MODE_DKV) {
         if (tid < 64) {
@@ -259,7 +277,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     };
     prefetch(g);
     for (int j = g; j < T; j += 2) {
-      const int n = j >> 1, t = tile_list[j];
+      const bool need_mask = (tile_list[j] & 0x8000) != 0;
       named_bar_sync(1 + g, 128);                        // the previous tile's statistics are no longer read
       if (MODE == MODE_DKV) {
         if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else { s_delta[tid - 64] = pre_f; }
@@ -268,57 +286,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       }
       named_bar_sync(1 + g, 128);
       prefetch(j + 2);
-      bool need_mask;
-      if (MODE == MODE_DKV) need_mask = masked && (row_hi > p.col_min[b * n_col_tiles + t]);
-      else need_mask = (masked && (p.col_max[b * n_col_tiles + t] > row_lo)) || (t * kCols + kCols > p.S_col);
+      const int n = j >> 1, pb = j % kNP;
       mbar_wait(&sdp_full[g], n & 1);
       tc_fence_after();
-      mbar_wait(&p_free[g], (n & 1) ^ 1);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + g * 128;
+      const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+      const uint32_t taddr = tmem_base + lane_base + g * 128;
+      uint32_t pw[32], dw[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld32(taddr + c * 32, sv);
         tmem_ld32(taddr + 64 + c * 32, dv);
         tmem_wait2(sv, dv);
-        if (c == 1) {
+        if (c == 1) {                                     // the score stage is in registers: hand it back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_free[g]);
+          if (lane == 0) mbar_arrive(&sdp_free[g]);
+        }
+        if (need_mask) {          // tile-level (warp-uniform) branch: only tiles that straddle a label boundary
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int cid = s_id[c * 32 + i];
+            const bool hide = (MODE == MODE_DKV) ? (my_id > cid) : (cid > my_id);
+            if (hide) sv[i] = 0xff800000u;              // -inf -> P = 0
+          }
         }
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          uint32_t pw[4], dw[4];
+          float lse8[8], dl8[8];
+          if (MODE == MODE_DKV) {
+            const float4 l0 = *reinterpret_cast<const float4*>(s_lse + c * 32 + g8 * 8);
+            const float4 l1 = *reinterpret_cast<const float4*>(s_lse + c * 32 + g8 * 8 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(s_delta + c * 32 + g8 * 8);
+            const float4 d1 = *reinterpret_cast<const float4*>(s_delta + c * 32 + g8 * 8 + 4);
+            lse8[0] = l0.x; lse8[1] = l0.y; lse8[2] = l0.z; lse8[3] = l0.w; lse8[4] = l1.x; lse8[5] = l1.y; lse8[6] = l1.z; lse8[7] = l1.w;
+            dl8[0] = d0.x; dl8[1] = d0.y; dl8[2] = d0.z; dl8[3] = d0.w; dl8[4] = d1.x; dl8[5] = d1.y; dl8[6] = d1.z; dl8[7] = d1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { lse8[e] = my_lse; dl8[e] = my_delta; }
+          }
 #pragma unroll
           for (int e2 = 0; e2 < 4; ++e2) {
-            float pv[2], ds[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = c * 32 + g8 * 8 + e2 * 2 + e;
-              float s = __uint_as_float(sv[g8 * 8 + e2 * 2 + e]);
-              const float d = __uint_as_float(dv[g8 * 8 + e2 * 2 + e]);
-              float lse, dl;
-              if (MODE == MODE_DKV) { lse = s_lse[col]; dl = s_delta[col]; } else { lse = my_lse; dl = my_delta; }
-              if (need_mask) {
-                const int cid = s_id[col];
-                const bool hide = (MODE == MODE_DKV) ? (my_id > cid) : (cid > my_id);
-                if (hide) s = -INFINITY;
-              }
-              pv[e] = fast_ex2(fmaf(s, p.scale_log2, -lse));
-              ds[e] = pv[e] * (d - dl);
-            }
-            pw[e2] = pack2(pv[0], pv[1]);
-            dw[e2] = pack2(ds[0], ds[1]);
+            const int i0 = g8 * 8 + e2 * 2;
+            const float p0 = fast_ex2(fmaf(__uint_as_float(sv[i0]), p.scale_log2, -lse8[e2 * 2]));
+            const float p1 = fast_ex2(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, -lse8[e2 * 2 + 1]));
+            const float s0 = p0 * (__uint_as_float(dv[i0]) - dl8[e2 * 2]);
+            const float s1 = p1 * (__uint_as_float(dv[i0 + 1]) - dl8[e2 * 2 + 1]);
+            if (MODE == MODE_DKV) pw[c * 16 + g8 * 4 + e2] = pack2(p0, p1);
+            dw[c * 16 + g8 * 4 + e2] = pack2(s0, s1);
           }
-          const int chunk = c * 4 + g8;                         // 16-byte chunk of this row (8 columns)
-          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
-          if (MODE == MODE_DKV) *reinterpret_cast<uint4*>(Pb + off) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-          *reinterpret_cast<uint4*>(Sb + off) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
         }
       }
-      fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core
+      // bf16 pairs -> operand buffer pb in TMEM (A operand of the accumulate MMAs, TS mode)
+      mbar_wait(&pbuf_free[pb], ((j / kNP) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t paddr = tmem_base + lane_base + 256 + pb * 64;
+      if (MODE == MODE_DKV) tmem_st32(paddr, pw);
+      tmem_st32(paddr + 32, dw);
+      tmem_wait_st();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[g]);
+      if (lane == 0) mbar_arrive(&p_ready[pb]);
     }
     // ---- epilogue: accumulators -> bf16 -> global ----
     mbar_wait(acc_full, 0);
@@ -328,7 +356,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       const int which = (MODE == MODE_DKV) ? g : 1;      // wg0 -> acc0 (dV), wg1 -> acc1 (dK / dQ)
       uint32_t acc[32];
       if (T > 0) {                                        // uniform: the whole warp executes the aligned TMEM load
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + 256 + which * 32, acc);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + 448 + which * 32, acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;"
                      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
                        "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]), "+r"(acc[14]), "+r"(acc[15]),
