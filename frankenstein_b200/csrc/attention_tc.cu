@@ -50,8 +50,8 @@ struct TcSmem {
   static constexpr int resA = 0;                       // 128 x 64 B
   static constexpr int resB = 8192;
   static constexpr int stream = 16384;                 // kNST x 16 KB: stA | stB | tA | tB (4 KB each)
-  static constexpr int stats = stream + kNST * 16384;  // [2 wg][lse | delta | id][64] x 4 B           // [2 wg][lse | delta | id][64] x 4 B
-  static constexpr int tiles = stats + 2 * 3 * 64 * 4; // uint16 visible-tile list
+  static constexpr int stats = stream + kNST * 16384;  // [2 wg][2 buffers][lse | delta | id][64] x 4 B           // [2 wg][lse | delta | id][64] x 4 B
+  static constexpr int tiles = stats + 2 * 2 * 3 * 64 * 4; // uint16 visible-tile list
   static constexpr int bars = tiles + kMaxTiles * 2;
   static constexpr int total = bars + 256;
 };
@@ -79,6 +79,27 @@ __device__ __forceinline__ void tmem_wait2(uint32_t (&a)[32], uint32_t (&b)[32])
                     "+r"(b[16]), "+r"(b[17]), "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]),
                     "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
                :: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait2_16(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                 "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
 template <int MODE>
@@ -246,9 +267,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     const int tid = (warp - 4 - g * 4) * 32 + lane;
     const int row = r0 + r;
     const bool row_ok = row < p.S_row;
-    float* s_lse = reinterpret_cast<float*>(smem + TcSmem::stats) + g * 192;
-    float* s_delta = s_lse + 64;
-    int* s_id = reinterpret_cast<int*>(s_lse + 128);
+    float* stats_base = reinterpret_cast<float*>(smem + TcSmem::stats) + g * 384;
     const float* lse_g = p.lse + (static_cast<long long>(b) * p.H + h) * p.Sq;
     const float* delta_g = p.delta + (static_cast<long long>(b) * p.H + h) * p.Sq;
     const int my_id = masked ? (row_ok ? p.row_id[static_cast<long long>(b) * p.S_row + row]
@@ -278,7 +297,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     prefetch(g);
     for (int j = g; j < T; j += 2) {
       const bool need_mask = (tile_list[j] & 0x8000) != 0;
-      named_bar_sync(1 + g, 128);                        // the previous tile's statistics are no longer read
+      // column statistics: double buffered per warpgroup, so one barrier per tile (write -> barrier -> read; the
+      // previous tile's readers use the other buffer)
+      float* s_lse = stats_base + ((j >> 1) & 1) * 192;
+      float* s_delta = s_lse + 64;
+      int* s_id = reinterpret_cast<int*>(s_lse + 128);
       if (MODE == MODE_DKV) {
         if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else { s_delta[tid - 64] = pre_f; }
       } else if (tid < 64) {
@@ -288,37 +311,46 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       prefetch(j + 2);
       const int n = j >> 1, pb = j % kNP;
       mbar_wait(&sdp_full[g], n & 1);
+      mbar_wait(&pbuf_free[pb], ((j / kNP) & 1) ^ 1);      // operand buffer pb no longer read by older MMAs
       tc_fence_after();
       const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
       const uint32_t taddr = tmem_base + lane_base + g * 128;
-      uint32_t pw[32], dw[32];
+      const uint32_t paddr = tmem_base + lane_base + 256 + pb * 64;
+      // 4 sub-chunks of 16 columns, software pipelined: the TMEM loads of sub-chunk i+1 are in flight while
+      // sub-chunk i is computed and its bf16 pairs are stored back to the operand buffer
+      uint32_t sv[2][16], dv[2][16];
+      tmem_ld16(taddr, sv[0]);
+      tmem_ld16(taddr + 64, dv[0]);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(taddr + c * 32, sv);
-        tmem_ld32(taddr + 64 + c * 32, dv);
-        tmem_wait2(sv, dv);
-        if (c == 1) {                                     // the score stage is in registers: hand it back
+      for (int i = 0; i < 4; ++i) {
+        const int cur = i & 1;
+        tmem_wait2_16(sv[cur], dv[cur]);
+        if (i < 3) {
+          tmem_ld16(taddr + (i + 1) * 16, sv[cur ^ 1]);
+          tmem_ld16(taddr + 64 + (i + 1) * 16, dv[cur ^ 1]);
+        } else {
+          // every column of this score stage is in registers: hand the stage back to the score-MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sdp_free[g]);
         }
         if (need_mask) {          // tile-level (warp-uniform) branch: only tiles that straddle a label boundary
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int cid = s_id[c * 32 + i];
+          for (int e = 0; e < 16; ++e) {
+            const int cid = s_id[i * 16 + e];
             const bool hide = (MODE == MODE_DKV) ? (my_id > cid) : (cid > my_id);
-            if (hide) sv[i] = 0xff800000u;              // -inf -> P = 0
+            if (hide) sv[cur][e] = 0xff800000u;              // -inf -> P = 0
           }
         }
+        uint32_t pw[8], dw[8];
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
+        for (int g8 = 0; g8 < 2; ++g8) {
           float lse8[8], dl8[8];
           if (MODE == MODE_DKV) {
-            const float4 l0 = *reinterpret_cast<const float4*>(s_lse + c * 32 + g8 * 8);
-            const float4 l1 = *reinterpret_cast<const float4*>(s_lse + c * 32 + g8 * 8 + 4);
-            const float4 d0 = *reinterpret_cast<const float4*>(s_delta + c * 32 + g8 * 8);
-            const float4 d1 = *reinterpret_cast<const float4*>(s_delta + c * 32 + g8 * 8 + 4);
+            const float4 l0 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8);
+            const float4 l1 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(s_delta + i * 16 + g8 * 8);
+            const float4 d1 = *reinterpret_cast<const float4*>(s_delta + i * 16 + g8 * 8 + 4);
             lse8[0] = l0.x; lse8[1] = l0.y; lse8[2] = l0.z; lse8[3] = l0.w; lse8[4] = l1.x; lse8[5] = l1.y; lse8[6] = l1.z; lse8[7] = l1.w;
             dl8[0] = d0.x; dl8[1] = d0.y; dl8[2] = d0.z; dl8[3] = d0.w; dl8[4] = d1.x; dl8[5] = d1.y; dl8[6] = d1.z; dl8[7] = d1.w;
           } else {
@@ -328,21 +360,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
 #pragma unroll
           for (int e2 = 0; e2 < 4; ++e2) {
             const int i0 = g8 * 8 + e2 * 2;
-            const float p0 = fast_ex2(fmaf(__uint_as_float(sv[i0]), p.scale_log2, -lse8[e2 * 2]));
-            const float p1 = fast_ex2(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, -lse8[e2 * 2 + 1]));
-            const float s0 = p0 * (__uint_as_float(dv[i0]) - dl8[e2 * 2]);
-            const float s1 = p1 * (__uint_as_float(dv[i0 + 1]) - dl8[e2 * 2 + 1]);
-            if (MODE == MODE_DKV) pw[c * 16 + g8 * 4 + e2] = pack2(p0, p1);
-            dw[c * 16 + g8 * 4 + e2] = pack2(s0, s1);
+            const float p0 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0]), p.scale_log2, -lse8[e2 * 2]));
+            const float p1 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0 + 1]), p.scale_log2, -lse8[e2 * 2 + 1]));
+            const float s0 = p0 * (__uint_as_float(dv[cur][i0]) - dl8[e2 * 2]);
+            const float s1 = p1 * (__uint_as_float(dv[cur][i0 + 1]) - dl8[e2 * 2 + 1]);
+            if (MODE == MODE_DKV) pw[g8 * 4 + e2] = pack2(p0, p1);
+            dw[g8 * 4 + e2] = pack2(s0, s1);
           }
         }
+        // bf16 pairs -> operand buffer pb (A operand of the accumulate MMAs, TS mode): 8 packed columns each
+        if (MODE == MODE_DKV) tmem_st8(paddr + i * 8, pw);
+        tmem_st8(paddr + 32 + i * 8, dw);
       }
-      // bf16 pairs -> operand buffer pb in TMEM (A operand of the accumulate MMAs, TS mode)
-      mbar_wait(&pbuf_free[pb], ((j / kNP) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t paddr = tmem_base + lane_base + 256 + pb * 64;
-      if (MODE == MODE_DKV) tmem_st32(paddr, pw);
-      tmem_st32(paddr + 32, dw);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
