@@ -102,6 +102,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_wait1_32(uint32_t (&a)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                 "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]),
+                 "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
+               :: "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_constant__ CUtensorMap tm_resB,
@@ -454,6 +463,321 @@ attn_transpose_kernel(const __nv_bfloat16* __restrict__ x, long long bs, long lo
   }
 }
 
+// ================================================================================================
+// Forward on tcgen05: CTA = 256 queries (two warpgroups, 128 rows each, one thread per row), streams 128-key
+// tiles (K as [keys][32] SW64, V as the transposed copy Vt [32][keys] SW128).  Per tile and warpgroup g:
+//   S_g = Q_g K^T (2 MMAs, N = 128) -> TMEM;  thread: pass 1 row max, pass 2 P = 2^(S c - m), row sum, bf16 pairs
+//   -> operand buffer in TMEM;  O_g += P V (8 TS-mode MMAs, N = 32) accumulating in TMEM.
+// Online softmax with LAZY rescaling: the running max m is only raised (and O, l rescaled) when a tile exceeds it
+// by more than 2^8 -- P <= 2^8 stays exact enough in bf16/fp32 and O / l is independent of the m that was used.
+// TMEM map: S_g at g*128 (128), P_g at 256 + g*64 (64), O_g at 384 + g*32 (32).
+// ================================================================================================
+constexpr int kFwdTileK = 128;
+constexpr int kFwdThreads = 384;
+constexpr float kRescaleSlack = 8.f;
+
+struct FwdSmem {
+  static constexpr int q = 0;                           // 2 x 128 x 64 B
+  static constexpr int stream = 16384;                  // kNST x 16 KB: K (8 KB) | Vt slab 0 | Vt slab 1 (4 KB each)
+  static constexpr int ids = stream + kNST * 16384;     // [2 wg][2 buffers][128] int
+  static constexpr int tiles = ids + 2 * 2 * 128 * 4;
+  static constexpr int bars = tiles + kMaxTiles * 2;
+  static constexpr int total = bars + 256;
+};
+
+struct FwdParams {
+  const int *qid, *kid;
+  const int *qmin, *qmax, *kmin, *kmax;                 // per-64-token tile label ranges
+  __nv_bfloat16* out;
+  float* lse;
+  long long o_bs, o_ts;
+  int B, H, Sq, Sk;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_vt, const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
+  uint64_t* q_full = bars;                  // [1]
+  uint64_t* st_full = bars + 1;             // [kNST]
+  uint64_t* st_empty = st_full + kNST;      // [kNST]  two arrivals: the P V MMAs of both warpgroups
+  uint64_t* s_full = st_empty + kNST;       // [2]     S_g written by the tensor core
+  uint64_t* s_free = s_full + 2;            // [2]     S_g read out (4 warps)
+  uint64_t* p_ready = s_free + 2;           // [2]     P_g written (4 warps)
+  uint64_t* p_free = p_ready + 2;           // [2]     P V MMAs of warpgroup g retired (O_g quiescent, P_g reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
+  int* n_tiles_slot = reinterpret_cast<int*>(p_free + 2) + 1;
+  uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + FwdSmem::tiles);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * 256;
+  const bool masked = p.qid != nullptr;
+  const int n_k_tiles = (p.Sk + kFwdTileK - 1) / kFwdTileK;
+  const int nq64 = (p.Sq + 63) / 64, nk64 = (p.Sk + 63) / 64;
+
+  // label ranges of the two warpgroups' rows (two 64-row entries each)
+  int wq_lo[2] = {0, 0}, wq_hi[2] = {0, 0};
+  if (masked) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int i0 = min(qt * 4 + g * 2, nq64 - 1), i1 = min(qt * 4 + g * 2 + 1, nq64 - 1);
+      wq_lo[g] = min(p.qmin[b * nq64 + i0], p.qmin[b * nq64 + i1]);
+      wq_hi[g] = max(p.qmax[b * nq64 + i0], p.qmax[b * nq64 + i1]);
+    }
+  }
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_vt); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kNST; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&p_free[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp == 3) {
+    // key tiles visible to at least one of the CTA's rows; bits 14 / 15 = warpgroup 0 / 1 must compare labels
+    const int cta_hi = max(wq_hi[0], wq_hi[1]);
+    int cnt = 0;
+    for (int base = 0; base < n_k_tiles; base += 32) {
+      const int t = base + lane;
+      bool vis = t < n_k_tiles;
+      int flags = 0;
+      if (vis) {
+        int kmn = 0, kmx = 0;
+        if (masked) {
+          const int i0 = min(t * 2, nk64 - 1), i1 = min(t * 2 + 1, nk64 - 1);
+          kmn = min(p.kmin[b * nk64 + i0], p.kmin[b * nk64 + i1]);
+          kmx = max(p.kmax[b * nk64 + i0], p.kmax[b * nk64 + i1]);
+          vis = kmn <= cta_hi;
+        }
+        const bool tail = t * kFwdTileK + kFwdTileK > p.Sk;
+        if ((masked && kmx > wq_lo[0]) || tail) flags |= 0x4000;
+        if ((masked && kmx > wq_lo[1]) || tail) flags |= 0x8000;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, vis);
+      if (vis) tile_list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(t | flags);
+      cnt += __popc(m);
+    }
+    if (lane == 0) *n_tiles_slot = cnt;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int T = *n_tiles_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 16384);
+      tma_load_4d(smem + FwdSmem::q, &tm_q, q_full, 0, h, q0, b);
+      tma_load_4d(smem + FwdSmem::q + 8192, &tm_q, q_full, 0, h, q0 + 128, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        const int t = tile_list[j] & 0x3fff;
+        uint8_t* st = smem + FwdSmem::stream + stage * 16384;
+        mbar_wait(&st_empty[stage], phase ^ 1);
+        mbar_expect_tx(&st_full[stage], 16384);
+        tma_load_4d(st, &tm_k, &st_full[stage], 0, h, t * kFwdTileK, b);
+        tma_load_2d(st + 8192, &tm_vt, &st_full[stage], t * kFwdTileK, (b * p.H + h) * 32);
+        tma_load_2d(st + 12288, &tm_vt, &st_full[stage], t * kFwdTileK + 64, (b * p.H + h) * 32);
+        if (++stage == kNST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ score-MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kFwdTileK);
+      const uint64_t dQ[2] = {umma_desc_sw64(smem_u32(smem + FwdSmem::q)), umma_desc_sw64(smem_u32(smem + FwdSmem::q + 8192))};
+      const uint32_t stream = smem_u32(smem + FwdSmem::stream);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      for (int j = 0; j < T; ++j) {
+        const int stage = j % kNST;
+        mbar_wait(&st_full[stage], (j / kNST) & 1);
+        const uint64_t dK = umma_desc_sw64(stream + stage * 16384);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&s_free[g], (j & 1) ^ 1);
+          tc_fence_after();
+          umma_bf16(tmem_base + g * 128, dQ[g], dK, idesc, 0u);
+          umma_bf16(tmem_base + g * 128, dQ[g] + 2, dK + 2, idesc, 1u);
+          umma_commit(&s_full[g]);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ P V MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
+      const uint32_t stream = smem_u32(smem + FwdSmem::stream);
+      for (int j = 0; j < T; ++j) {
+        const int stage = j % kNST;
+        const uint64_t dV0 = umma_desc_sw128(stream + stage * 16384 + 8192), dV1 = umma_desc_sw128(stream + stage * 16384 + 12288);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_ready[g], j & 1);
+          tc_fence_after();
+          const uint32_t pa = tmem_base + 256 + g * 64, oa = tmem_base + 384 + g * 32;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ts(oa, pa + kk * 8, (kk < 4 ? dV0 : dV1) + 2 * (kk & 3), idesc, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&p_free[g]);
+          umma_commit(&st_empty[stage]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ softmax warpgroups ================================
+    const int g = (warp - 4) >> 2;
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int tid = (warp - 4 - g * 4) * 32 + lane;
+    const int row = q0 + g * 128 + r;
+    const bool row_ok = row < p.Sq;
+    const int my_id = masked ? (row_ok ? p.qid[static_cast<long long>(b) * p.Sq + row] : -0x7fffffff) : 0;
+    int* ids_base = reinterpret_cast<int*>(smem + FwdSmem::ids) + g * 256;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base + g * 128;
+    const uint32_t p_addr = tmem_base + lane_base + 256 + g * 64;
+    const uint32_t o_addr = tmem_base + lane_base + 384 + g * 32;
+    float m_run = -INFINITY, l_run = 0.f;
+    int pre_i = 0;
+    auto prefetch = [&](int j) {
+      if (j >= T) return;
+      const int c = (tile_list[j] & 0x3fff) * kFwdTileK + tid;
+      pre_i = (c < p.Sk) ? (masked ? p.kid[static_cast<long long>(b) * p.Sk + c] : 0) : 0x7fffffff;
+    };
+    prefetch(0);
+    for (int j = 0; j < T; ++j) {
+      const bool need_mask = (tile_list[j] & (g == 0 ? 0x4000 : 0x8000)) != 0;
+      int* s_id = ids_base + (j & 1) * 128;
+      s_id[tid] = pre_i;
+      named_bar_sync(1 + g, 128);
+      prefetch(j + 1);
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum of the (masked) scores; TMEM loads double buffered (next chunk in flight) ----
+      float mx = -INFINITY;
+      uint32_t sv[2][32];
+      tmem_ld32(s_addr, sv[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cur = c & 1;
+        tmem_wait1_32(sv[cur]);
+        tmem_ld32(s_addr + ((c + 1) & 3) * 32, sv[cur ^ 1]);      // c == 3: chunk 0 again, for pass 2
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (s_id[c * 32 + i] > my_id) sv[cur][i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[cur][i]), __uint_as_float(sv[cur][i + 1])));
+      }
+      // ---- running maximum with lazy rescaling ----
+      const float m_tile = mx * p.scale_log2;
+      const bool raise = m_tile > m_run + kRescaleSlack || m_run == -INFINITY;
+      const float m_new = raise ? fmaxf(m_run, m_tile) : m_run;
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = (raise && m_run != -INFINITY) ? fast_ex2(m_run - m_use) : 1.f;
+      // O_g is quiescent once the previous tile's P V MMAs have retired; P_g is then reusable as well
+      mbar_wait(&p_free[g], (j & 1) ^ 1);
+      tc_fence_after();
+      const bool rescale = j > 0 && __any_sync(0xffffffffu, alpha != 1.f);
+      l_run *= alpha;
+      m_run = m_new;
+      // ---- pass 2: P = 2^(S c - m), row sum, bf16 pairs into the operand buffer ----
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cur = c & 1;                            // chunk 0 was requested by the last step of pass 1
+        tmem_wait1_32(sv[cur]);
+        if (c < 3) {
+          tmem_ld32(s_addr + (c + 1) * 32, sv[cur ^ 1]);
+        } else {                                          // S_g fully consumed: the next tile's scores may land
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[g]);
+        }
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (s_id[c * 32 + i] > my_id) sv[cur][i] = 0xff800000u;
+        }
+        uint32_t pw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = fast_ex2(fmaf(__uint_as_float(sv[cur][2 * i]), p.scale_log2, -m_use));
+          const float p1 = fast_ex2(fmaf(__uint_as_float(sv[cur][2 * i + 1]), p.scale_log2, -m_use));
+          rs += p0 + p1;
+          pw[i] = pack2(p0, p1);
+        }
+        tmem_st16(p_addr + c * 16, pw);
+      }
+      if (rescale) {                                      // rare: O_g *= alpha (warp-uniform branch)
+        uint32_t ov[32];
+        tmem_ld32(o_addr, ov);
+        tmem_wait1_32(ov);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+        tmem_st32(o_addr, ov);
+      }
+      l_run += rs;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+    }
+    // ---- epilogue: O / l -> bf16, LSE ----
+    if (T > 0) {
+      mbar_wait(&p_free[g], (T & 1) ^ 1);              // the last P V MMAs have retired
+      tc_fence_after();
+    }
+    uint32_t ov[32];
+    if (T > 0) {
+      tmem_ld32(o_addr, ov);
+      tmem_wait1_32(ov);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) ov[i] = 0u;
+    }
+    if (row_ok) {
+      const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+      __nv_bfloat16* dst = p.out + b * p.o_bs + static_cast<long long>(row) * p.o_ts + h * 32;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w[e] = pack2(__uint_as_float(ov[c4 * 8 + e * 2]) * inv, __uint_as_float(ov[c4 * 8 + e * 2 + 1]) * inv);
+        *reinterpret_cast<uint4*>(dst + c4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      if (p.lse != nullptr)
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + row] = (l_run > 0.f) ? m_run + log2f(l_run) : INFINITY;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace fk
 
 using namespace fk;
@@ -543,5 +867,42 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     ++n;
   }
   fk_count_launch(n);
+  return FK_OK;
+}
+
+// Forward on tcgen05.  vt = fk_attn_transpose(v) ([B][H][32][Sp]); same label / range conventions as fk_attn_forward.
+FK_API int fk_attn_forward_tc(const void* q, const void* k, const void* vt, int Sp, void* out, float* lse, int B, int H, int S,
+                              int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long o_bs,
+                              long long o_ts, const int* qid, const int* kid, const int* qmin, const int* qmax, const int* kmin,
+                              const int* kmax, float scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(head_dim == 32, "fk_attn_forward_tc: only head_dim 32 is built");
+  FK_REQUIRE(q && k && vt && out && B > 0 && H > 0 && S > 0, "fk_attn_forward_tc: bad argument");
+  FK_REQUIRE((qid == nullptr) == (kid == nullptr), "fk_attn_forward_tc: qid and kid go together");
+  FK_REQUIRE(qid == nullptr || (qmin && qmax && kmin && kmax), "fk_attn_forward_tc: label ranges missing");
+  FK_REQUIRE((S + kFwdTileK - 1) / kFwdTileK <= kMaxTiles && S < (1 << 20), "fk_attn_forward_tc: sequence too long");
+  FK_REQUIRE(Sp >= S && Sp % 8 == 0, "fk_attn_forward_tc: Sp must be >= S and a multiple of 8");
+  FK_REQUIRE(o_ts % 8 == 0 && o_bs % 8 == 0, "fk_attn_forward_tc: output strides must keep 16-byte alignment");
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::total) != cudaSuccess) {
+      fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
+      return FK_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  CUtensorMap mQ, mK, mVt;
+  int rc = 0;
+  rc |= make_tmap_heads_sw64(&mQ, q, B, S, H, q_bs, q_ts, 128);
+  rc |= make_tmap_heads_sw64(&mK, k, B, S, H, k_bs, k_ts, kFwdTileK);
+  rc |= make_tmap_bf16_sw128(&mVt, vt, static_cast<uint64_t>(B) * H * 32, static_cast<uint64_t>(Sp), 32);
+  if (rc != 0) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
+  FwdParams p = {};
+  p.qid = qid; p.kid = kid; p.qmin = qmin; p.qmax = qmax; p.kmin = kmin; p.kmax = kmax;
+  p.out = static_cast<__nv_bfloat16*>(out); p.lse = lse; p.o_bs = o_bs; p.o_ts = o_ts;
+  p.B = B; p.H = H; p.Sq = S; p.Sk = S; p.scale_log2 = scale * 1.4426950408889634f;
+  attn_fwd_tc_kernel<<<dim3((S + 255) / 256, H, B), kFwdThreads, FwdSmem::total, stream>>>(mQ, mK, mVt, p);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
   return FK_OK;
 }

@@ -18,6 +18,7 @@ import os
 
 # attention backward implementation: "tc" = tcgen05/TMEM/TMA kernels (attention_tc.cu), "legacy" = mma.sync kernels
 ATTN_BWD_IMPL = os.environ.get("FK_ATTN_BWD", "tc")
+ATTN_FWD_IMPL = os.environ.get("FK_ATTN_FWD", "tc")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -203,13 +204,23 @@ class _AttnQKVFn(torch.autograd.Function):
         need_grad = qkv.requires_grad
         lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
         m = mask
-        with timed("attn_fwd"):
-          check(lib().fk_attn_forward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, S, hd,
-                                    q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
-                                    out.stride(0), out.stride(1),
-                                    ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0,
-                                    ptr(m.qmax) if m else 0, ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0,
-                                    float(scale), stream()), "fk_attn_forward")
+        margs = (ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0, ptr(m.qmax) if m else 0,
+                 ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0, float(scale))
+        if ATTN_FWD_IMPL == "legacy":
+            with timed("attn_fwd"):
+                check(lib().fk_attn_forward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, S, hd,
+                                            q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                            out.stride(0), out.stride(1), *margs, stream()), "fk_attn_forward")
+        else:
+            Sp = (S + 7) // 8 * 8
+            vt = torch.empty(B, H, hd, Sp, device=qkv.device, dtype=torch.bfloat16)
+            with timed("attn_transpose"):
+                check(lib().fk_attn_transpose(ptr(v), v.stride(0), v.stride(1), B, S, H, hd, ptr(vt), Sp, stream()),
+                      "fk_attn_transpose")
+            with timed("attn_fwd"):
+                check(lib().fk_attn_forward_tc(ptr(q), ptr(k), ptr(vt), Sp, ptr(out), ptr(lse), B, H, S, hd,
+                                               q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
+                                               *margs, stream()), "fk_attn_forward_tc")
         ctx.save_for_backward(qkv, out, lse)
         ctx.rope, ctx.mask, ctx.scale, ctx.H = rope, mask, scale, H
         return out

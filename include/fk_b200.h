@@ -146,6 +146,12 @@ int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void*
                         long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
                         const int* kmin, const int* kmax, float scale, int parts, void* stream);
 
+/* tcgen05 / TMEM / TMA forward (attention_tc.cu): vt = fk_attn_transpose(v) ([B][H][32][Sp]); Sq == Sk == S. */
+int fk_attn_forward_tc(const void* q, const void* k, const void* vt, int Sp, void* out, float* lse, int B, int H, int S,
+                       int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long o_bs,
+                       long long o_ts, const int* qid, const int* kid, const int* qmin, const int* qmax, const int* kmin,
+                       const int* kmax, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

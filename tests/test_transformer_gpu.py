@@ -44,6 +44,7 @@ def _labels(kind, B, S, dev, g):
 def test_attention_fwd_bwd(kind, B, S, H, impl, monkeypatch):
     from frankenstein_b200 import ops
     monkeypatch.setattr(ops, "ATTN_BWD_IMPL", impl)
+    monkeypatch.setattr(ops, "ATTN_FWD_IMPL", impl)
     g = torch.Generator().manual_seed(B * 1000 + S)
     dev = torch.device("cuda")
     qkv = (torch.randn(B, S, 3 * H * 32, generator=g) * 1.5).to(dev).to(torch.bfloat16)
