@@ -22,8 +22,8 @@
 // cut into gridDim.x contiguous ranges (persistent CTAs, perfect balance to within one unit), so a
 // CTA covers at most a few row blocks ("segments") and writes one candidate slot per segment.
 //
-// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 =
-// TMEM allocator, warps 4-19 = epilogue (TMEM lane quarter x accumulator half x column half).
+// Warp roles (640 threads): warp 0 = TMA producer, warps 1 and 3 = MMA issuers (one thread each, one per
+// accumulator half), warp 2 = TMEM allocator, warps 4-19 = epilogue (TMEM lane quarter x accumulator half x column half).
 #include "common.cuh"
 #include "tma_host.cuh"
 
@@ -107,9 +107,9 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t* empty = bars + kMaxStages;      // [kMaxStages]
   uint64_t* x_full = bars + 2 * kMaxStages;
   uint64_t* x_empty = x_full + 1;
-  uint64_t* tmem_full = x_full + 2;         // [2]
-  uint64_t* tmem_empty = x_full + 4;        // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(x_full + 6);
+  uint64_t* tmem_full = x_full + 2;         // [2 stages][2 halves]
+  uint64_t* tmem_empty = x_full + 6;        // [2 stages][2 halves]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(x_full + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -120,13 +120,13 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.nstage; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], 2);        // both MMA issuers (one per accumulator half) release a slab
     }
     mbar_init(x_full, 1);
-    mbar_init(x_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    mbar_init(x_empty, 2);
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 16);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], 8);   // one arrival per epilogue warp of that half
     }
     fence_mbar_init();
   }
@@ -167,11 +167,15 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         u += nt;
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 || warp == 3) {
+    // ================================ MMA issuers ================================
+    // Two issuing threads, one per accumulator half (rows 0-127 / 128-255): measured on B200 one thread sustains
+    // one tcgen05.mma per ~100 cycles while the tensor core accepts an M128 x N128 x K16 MMA every 64
+    // (scripts/microbench/umma_rate.cu), so a single issuer caps the kernel at ~60 % of the MMA rate.
     if (lane == 0) {
+      const int h = (warp == 1) ? 0 : 1;
       constexpr uint32_t idesc = umma_idesc_bf16(128, kBN);
-      const uint32_t xs_addr = smem_u32(Xs), bs_addr = smem_u32(Bs);
+      const uint32_t xs_addr = smem_u32(Xs) + h * (128 * 128), bs_addr = smem_u32(Bs);
       int stage = 0;
       uint32_t phase = 0, seg = 0, tc = 0;
       for (long long u = u_begin; u < u_end; ++seg) {
@@ -181,25 +185,21 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc_fence_after();
         for (int t = 0; t < nt; ++t, ++tc) {
           const uint32_t as = tc & 1;
-          mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
+          mbar_wait(&tmem_empty[as * 2 + h], ((tc >> 1) & 1) ^ 1);
           tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (h * 2 + as) * kBN;
           for (int ks = 0; ks < p.nslab; ++ks) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(xs_addr + ks * kXSlabBytes);
+            const uint64_t bdesc = umma_desc_sw128(bs_addr + stage * kBSlabBytes);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t d_tmem = tmem_base + (h * 2 + as) * kBN;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t adesc = umma_desc_sw128(xs_addr + ks * kXSlabBytes + h * (128 * 128) + kk * 32);
-                const uint64_t bdesc = umma_desc_sw128(bs_addr + stage * kBSlabBytes + kk * 32);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0);
-              }
-            }
-            umma_commit(&empty[stage]);   // slab free once these MMAs retire
+            for (int kk = 0; kk < 4; ++kk)      // a K step of 16 bf16 = 32 bytes = +2 in the (address >> 4) field
+              umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (ks | kk) != 0);
+            umma_commit(&empty[stage]);   // slab free once the MMAs of both halves have retired (2 arrivals)
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full[as]);
+          umma_commit(&tmem_full[as * 2 + h]);
         }
         umma_commit(x_empty);
         u += nt;
@@ -231,7 +231,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (have_next) c2_next = __ldg(p.c2pad + ((u + 1) % p.T) * kBN + etid);
       const float* my_c2 = c2s + as * kBN + cpart * 64;
       const uint32_t tag = static_cast<uint32_t>(t - t_seg0) * 2u;
-      mbar_wait(&tmem_full[as], (tc >> 1) & 1);
+      mbar_wait(&tmem_full[as * 2 + h], (tc >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (h * 2 + as) * kBN + cpart * 64;
       const long long row = static_cast<long long>(rb) * kBM + h * 128 + q * 32 + lane;
@@ -253,7 +253,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // all TMEM reads of this accumulator stage are done: hand it back before the last scan
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) mbar_arrive(&tmem_empty[as * 2 + h]);
       scan16(rb2, my_c2 + 48, p.alpha, keep_mask, tag + 1u, m, 16, dbg ? dbg + 48 : nullptr);
       if (have_next) c2s[(as ^ 1) * kBN + etid] = c2_next;
       named_bar_sync(1, kEpilogueThreads);      // c2 of the next tile visible; this tile's c2 reads finished
