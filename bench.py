@@ -312,9 +312,9 @@ def main():
         # (its S / dP re-computation is overhead of the two-kernel split and is not counted as useful work)
         alg = {"vq_search": 2.0 * n_vq * VQ_K * VQ_D, "attn_fwd": 2 * qk, "attn_bwd_dkv": 4 * qk, "attn_bwd_dq": 1 * qk}
         names = {"vq_search": "fk::vq_search_kernel (tcgen05/TMEM/TMA nearest-codeword search)",
-                 "attn_fwd": "fk::attn_fwd_kernel (label-mask flash attention forward, mma.sync bf16)",
-                 "attn_bwd_dkv": "fk::attn_bwd_dkv_kernel (label-mask flash attention dK/dV, mma.sync bf16)",
-                 "attn_bwd_dq": "fk::attn_bwd_dq_kernel (label-mask flash attention dQ, mma.sync bf16)"}
+                 "attn_fwd": "fk::attn_fwd_tc_kernel (label-mask flash attention forward, tcgen05/TMEM/TMA)",
+                 "attn_bwd_dkv": "fk::attn_bwd_tc_kernel<DKV> (label-mask flash attention dK/dV, tcgen05/TMEM/TMA)",
+                 "attn_bwd_dq": "fk::attn_bwd_tc_kernel<DQ> (label-mask flash attention dQ, tcgen05/TMEM/TMA)"}
         # ncu --set full captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
         traffic = {"vq_search": NCU_TRAFFIC.get("vq_search")}
         kern = {}
