@@ -228,6 +228,33 @@ class Block(nn.Module):
         return x
 
 
+def run_blocks(blocks, h, attn_mask=None, rope=None, final_norm=None, final_dtype=torch.float32):
+    """A stack of pre-LN Blocks on the fp32 residual stream `h` with every `x = x + branch` fused into the LayerNorm
+    that follows it (ops.add_layer_norm): identical math to calling the Blocks one after another
+    (models/brainformer.py:242-245, 345-351), one pass over the residual stream per add+norm instead of three.
+    Returns (h, y) where y = final_norm(h) if final_norm is given, else None."""
+    n = len(blocks)
+    if n == 0:
+        return h, (final_norm(h, out_dtype=final_dtype) if final_norm is not None else None)
+    if h.dtype != torch.float32 or not isinstance(blocks[0].ln_1, _KernelLayerNorm):
+        for blk in blocks:                                   # generic path (e.g. RMSNorm blocks, bf16 streams)
+            h = blk(h, attn_mask=attn_mask, rope=rope)
+        return h, (final_norm(h, out_dtype=final_dtype) if final_norm is not None else None)
+    y = blocks[0].ln_1(h)
+    for i, blk in enumerate(blocks):
+        a = blk.attn(y, attn_mask, rope)
+        h, y = ops.add_layer_norm(h, a, blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
+        m = blk.mlp(y)
+        if i + 1 < n:
+            nxt = blocks[i + 1].ln_1
+            h, y = ops.add_layer_norm(h, m, nxt.weight, nxt.bias, nxt.eps)
+        elif final_norm is not None:
+            h, y = ops.add_layer_norm(h, m, final_norm.weight, final_norm.bias, final_norm.eps, final_dtype)
+        else:
+            h, y = h + m, None
+    return h, y
+
+
 class CrossBlock(nn.Module):
     """cross-attention + MLP, then a self-attention Block  (models/brainformer.py:247-268)."""
 
@@ -318,9 +345,8 @@ class Encoder(nn.Module):
             ids = ((torch.arange(n_tokens, device=x.device) + first) // self.n_electrodes).to(torch.int32)
             mask = LabelMask(ids[None].expand(b, n_tokens).contiguous())
         rope = RopeSpec(self.rope_table(), None, self.block_size - n_tokens)
-        for block in self.transformer.h:
-            h = block(h, attn_mask=mask, rope=rope, kv_cache=kv_cache)
-        return self.transformer.ln_f(h, out_dtype=torch.float32)
+        _, y = run_blocks(self.transformer.h, h, mask, rope, self.transformer.ln_f)
+        return y
 
 
 class MAE(nn.Module):
@@ -375,17 +401,14 @@ class MAE(nn.Module):
         tokens = enc.embed(kept) + enc.spatial_pos_embedding[0][unmasked_indices]
         mask = LabelMask((unmasked_indices // enc.n_electrodes).to(torch.int32))
         rope = RopeSpec(enc.rope_table(), unmasked_indices, 0)
-        for block in enc.transformer.h:
-            tokens = block(tokens, attn_mask=mask, rope=rope)
-        tokens = enc.transformer.ln_f(tokens, out_dtype=torch.float32)
+        _, tokens = run_blocks(enc.transformer.h, tokens, mask, rope, enc.transformer.ln_f)
 
         # ---- decoder on all tokens (no mask, no rope); pos-emb order is cat[unmasked, masked] as in the reference ----
         dec = torch.zeros(b, n_tokens, self.decoder_dim, device=x.device, dtype=tokens.dtype)
         dec[rows, unmasked_indices] = self.decoder.emb(tokens)
         dec[rows, masked_indices] = self.mask_token.to(dec.dtype)
         dec = dec + self.decoder_pos_emb(torch.cat([unmasked_indices, masked_indices], 1))
-        for block in self.decoder.h:
-            dec = block(dec)
+        dec, _ = run_blocks(self.decoder.h, dec)
 
         pred = _linear_bf16(dec[rows, masked_indices], self.to_signals.weight, self.to_signals.bias).float()
         target = x[rows, masked_indices]

@@ -40,7 +40,10 @@ template <> struct Vec4<__nv_bfloat16> {
 template <typename TIn, typename TOut, int MAXV>
 __global__ void __launch_bounds__(kNormWarps * 32)
 norm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, TOut* __restrict__ y,
-                float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int D, float eps, int rms) {
+                float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int D, float eps, int rms,
+                const __nv_bfloat16* __restrict__ delta = nullptr, float* __restrict__ x_out = nullptr) {
+  // delta / x_out (fp32 residual stream only): x_new = x + delta is written to x_out and normalised, fusing the
+  // residual add of the transformer block into the norm that follows it
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kNormWarps + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -50,8 +53,17 @@ norm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const fl
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int d = (i * 32 + lane) * 4;
-    if (d < D) { Vec4<TIn>::load(xr + d, v[i]); s += v[i][0] + v[i][1] + v[i][2] + v[i][3]; }
-    else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+    if (d < D) {
+      Vec4<TIn>::load(xr + d, v[i]);
+      if (delta != nullptr) {
+        float dl[4];
+        Vec4<__nv_bfloat16>::load(delta + row * D + d, dl);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] += dl[j];
+        Vec4<float>::store(x_out + row * D + d, v[i]);
+      }
+      s += v[i][0] + v[i][1] + v[i][2] + v[i][3];
+    } else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
   }
   float mean = 0.f;
   if (!rms) mean = warp_sum(s) / D;
@@ -93,7 +105,9 @@ template <typename TIn, typename TG, typename TDx, int MAXV>
 __global__ void __launch_bounds__(kNormWarps * 32)
 norm_bwd_kernel(const TIn* __restrict__ x, const TG* __restrict__ g, const float* __restrict__ w, const float* __restrict__ mean_in,
                 const float* __restrict__ rstd_in, TDx* __restrict__ dx, float* __restrict__ dw_part, float* __restrict__ db_part,
-                long long M, int D, int rms) {
+                long long M, int D, int rms, const float* __restrict__ g_res = nullptr, __nv_bfloat16* __restrict__ dx_bf16 = nullptr) {
+  // g_res: gradient that reaches x through the residual path (added to dx); dx_bf16: second copy of dx for the
+  // bf16 branch of the fused residual add (x_new = x + delta  =>  d delta = d x = dx)
   extern __shared__ float sm[];        // [kNormWarps][2][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float dw[MAXV][4], db[MAXV][4], wv[MAXV][4];
@@ -139,7 +153,14 @@ norm_bwd_kernel(const TIn* __restrict__ x, const TG* __restrict__ g, const float
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = rstd * (gw[i][j] - s1 - xh[i][j] * s2);
+        if (g_res != nullptr) {
+          float gr[4];
+          Vec4<float>::load(g_res + row * D + d, gr);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] += gr[j];
+        }
         Vec4<TDx>::store(dx + row * D + d, o);
+        if (dx_bf16 != nullptr) Vec4<__nv_bfloat16>::store(dx_bf16 + row * D + d, o);
       }
     }
   }
@@ -227,28 +248,29 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ h13, const __nv_bfloat16* __
 
 template <typename TIn, typename TOut>
 static int launch_norm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, long long M, int D,
-                           float eps, int rms, cudaStream_t stream) {
+                           float eps, int rms, cudaStream_t stream, const __nv_bfloat16* delta = nullptr, float* x_out = nullptr) {
   const unsigned grid = static_cast<unsigned>((M + kNormWarps - 1) / kNormWarps);
   const TIn* xi = static_cast<const TIn*>(x);
   TOut* yo = static_cast<TOut*>(y);
-  if (D <= 128) norm_fwd_kernel<TIn, TOut, 1><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms);
-  else if (D <= 256) norm_fwd_kernel<TIn, TOut, 2><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms);
-  else if (D <= 512) norm_fwd_kernel<TIn, TOut, 4><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms);
-  else if (D <= 1024) norm_fwd_kernel<TIn, TOut, 8><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms);
+  if (D <= 128) norm_fwd_kernel<TIn, TOut, 1><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out);
+  else if (D <= 256) norm_fwd_kernel<TIn, TOut, 2><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out);
+  else if (D <= 512) norm_fwd_kernel<TIn, TOut, 4><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out);
+  else if (D <= 1024) norm_fwd_kernel<TIn, TOut, 8><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out);
   else return FK_ERR_UNSUPPORTED;
   return FK_OK;
 }
 
 template <typename TIn, typename TG, typename TDx>
 static int launch_norm_bwd(const void* x, const void* g, const float* w, const float* mean, const float* rstd, void* dx,
-                           float* dwp, float* dbp, long long M, int D, int rms, int grid, cudaStream_t stream) {
+                           float* dwp, float* dbp, long long M, int D, int rms, int grid, cudaStream_t stream,
+                           const float* g_res = nullptr, __nv_bfloat16* dx_bf16 = nullptr) {
   const TIn* xi = static_cast<const TIn*>(x);
   const TG* gi = static_cast<const TG*>(g);
   TDx* dxo = static_cast<TDx*>(dx);
   const size_t smem = static_cast<size_t>(kNormWarps) * 2 * D * sizeof(float);
-  if (D <= 128) norm_bwd_kernel<TIn, TG, TDx, 1><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms);
-  else if (D <= 256) norm_bwd_kernel<TIn, TG, TDx, 2><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms);
-  else if (D <= 512) norm_bwd_kernel<TIn, TG, TDx, 4><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms);
+  if (D <= 128) norm_bwd_kernel<TIn, TG, TDx, 1><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
+  else if (D <= 256) norm_bwd_kernel<TIn, TG, TDx, 2><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
+  else if (D <= 512) norm_bwd_kernel<TIn, TG, TDx, 4><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
   else return FK_ERR_UNSUPPORTED;
   return FK_OK;
 }
@@ -311,6 +333,43 @@ FK_API int fk_swiglu_backward(const void* h13, const void* gy, void* dh13, long 
   const long long n = M * H / 8;
   swiglu_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(h13), static_cast<const __nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(dh13), M, H);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+// Fused residual add + norm (fp32 residual stream): x_new = x + delta (bf16), y = norm(x_new).  Replaces the pair
+// `x = x + branch(...)` ; `ln(x)` of models/brainformer.py:243-244 (one pass over the residual stream instead of two).
+FK_API int fk_add_norm_forward(const float* x, const void* delta_bf16, const float* weight, const float* bias, float* x_out,
+                               void* y, int y_dtype, float* mean, float* rstd, long long M, int D, float eps, int rms,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(x && delta_bf16 && weight && x_out && y && rstd && M > 0 && D > 0 && D % 4 == 0, "fk_add_norm_forward: bad argument");
+  FK_REQUIRE(rms || mean, "fk_add_norm_forward: LayerNorm needs the mean buffer");
+  const __nv_bfloat16* dl = static_cast<const __nv_bfloat16*>(delta_bf16);
+  int rc = FK_ERR_UNSUPPORTED;
+  if (y_dtype == 1) rc = launch_norm_fwd<float, __nv_bfloat16>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream, dl, x_out);
+  else if (y_dtype == 0) rc = launch_norm_fwd<float, float>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream, dl, x_out);
+  if (rc != FK_OK) { fk_set_last_error("fk_add_norm_forward: unsupported dtype or D > 1024", __FILE__, __LINE__); return rc; }
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+// Backward of the fused op: dx = norm_backward(g_y) + g_res (g_res nullable: gradient arriving at x_new through the
+// residual path); writes dx as fp32 (gradient of x) and, if dx_bf16 != NULL, a bf16 copy (gradient of delta).
+FK_API int fk_add_norm_backward(const float* x_new, const void* g_y, int g_dtype, const float* g_res, const float* weight,
+                                const float* mean, const float* rstd, float* dx, void* dx_bf16, float* dw_part, float* db_part,
+                                long long M, int D, int rms, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(x_new && g_y && weight && rstd && dx && dw_part && M > 0 && D > 0 && D % 4 == 0, "fk_add_norm_backward: bad argument");
+  FK_REQUIRE(rms || mean, "fk_add_norm_backward: LayerNorm needs the mean buffer");
+  const int grid = fk_norm_backward_grid();
+  __nv_bfloat16* db16 = static_cast<__nv_bfloat16*>(dx_bf16);
+  int rc = FK_ERR_UNSUPPORTED;
+  if (g_dtype == 1) rc = launch_norm_bwd<float, __nv_bfloat16, float>(x_new, g_y, weight, mean, rstd, dx, dw_part, db_part, M, D, rms, grid, stream, g_res, db16);
+  else if (g_dtype == 0) rc = launch_norm_bwd<float, float, float>(x_new, g_y, weight, mean, rstd, dx, dw_part, db_part, M, D, rms, grid, stream, g_res, db16);
+  if (rc != FK_OK) { fk_set_last_error("fk_add_norm_backward: unsupported dtype or D > 512", __FILE__, __LINE__); return rc; }
   FK_CHECK_LAUNCH();
   fk_count_launch();
   return FK_OK;

@@ -71,6 +71,65 @@ class _NormFn(torch.autograd.Function):
         return dx.to(ctx.in_dtype), dw, db, None, None, None
 
 
+class _AddNormFn(torch.autograd.Function):
+    """(x_new, y) = (x + delta, norm(x + delta)) in one pass over the fp32 residual stream; backward fuses the norm
+    backward with the residual-gradient add and emits the bf16 gradient of the delta branch."""
+
+    @staticmethod
+    def forward(ctx, x, delta, weight, bias, eps, rms, out_dtype):
+        require_cuda(x, delta, weight)
+        require_device()
+        if x.dtype != torch.float32 or delta.dtype != torch.bfloat16:
+            raise FkError("add_norm expects an fp32 residual stream and a bf16 branch output")
+        D = x.shape[-1]
+        xc, dc = x.contiguous(), delta.contiguous()
+        M = xc.numel() // D
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        x_new = torch.empty_like(xc)
+        y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+        mean = None if rms else torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        check(lib().fk_add_norm_forward(ptr(xc), ptr(dc), ptr(w), ptr(b), ptr(x_new), ptr(y), _DT[out_dtype], ptr(mean),
+                                        ptr(rstd), M, D, float(eps), int(rms), stream()), "fk_add_norm_forward")
+        ctx.save_for_backward(x_new, w, mean if mean is not None else torch.empty(0, device=x.device), rstd)
+        ctx.rms, ctx.has_bias, ctx.w_dtype = rms, bias is not None, weight.dtype
+        return x_new, y
+
+    @staticmethod
+    def backward(ctx, g_xnew, g_y):
+        x_new, w, mean, rstd = ctx.saved_tensors
+        D = x_new.shape[-1]
+        M = x_new.numel() // D
+        if g_y is None:
+            g_y = torch.zeros(x_new.shape, device=x_new.device, dtype=torch.bfloat16)
+        g_y = g_y.contiguous()
+        if g_y.dtype not in _DT:
+            g_y = g_y.float()
+        if g_xnew is not None:
+            g_xnew = g_xnew.contiguous().float()
+        dx = torch.empty_like(x_new)
+        dx16 = torch.empty(x_new.shape, device=x_new.device, dtype=torch.bfloat16)
+        nb = lib().fk_norm_backward_grid()
+        dwp = torch.empty(nb, D, device=x_new.device, dtype=torch.float32)
+        dbp = torch.empty(nb, D, device=x_new.device, dtype=torch.float32) if ctx.has_bias else None
+        check(lib().fk_add_norm_backward(ptr(x_new), ptr(g_y), _DT[g_y.dtype], ptr(g_xnew), ptr(w),
+                                         ptr(mean) if not ctx.rms else 0, ptr(rstd), ptr(dx), ptr(dx16), ptr(dwp), ptr(dbp),
+                                         M, D, int(ctx.rms), stream()), "fk_add_norm_backward")
+        dw = dwp.sum(0).to(ctx.w_dtype)
+        db = dbp.sum(0).to(ctx.w_dtype) if ctx.has_bias else None
+        return dx, dx16, dw, db, None, None, None
+
+
+def add_layer_norm(x, delta, weight, bias, eps=1e-5, out_dtype=torch.bfloat16):
+    """x_new = x + delta; y = LayerNorm(x_new)  ->  (x_new fp32, y)."""
+    return _AddNormFn.apply(x, delta, weight, bias, eps, False, out_dtype)
+
+
+def add_rms_norm(x, delta, weight, eps=1e-6, out_dtype=torch.bfloat16):
+    return _AddNormFn.apply(x, delta, weight, None, eps, True, out_dtype)
+
+
 def layer_norm(x, weight, bias, eps=1e-5, out_dtype=torch.bfloat16):
     return _NormFn.apply(x, weight, bias, eps, False, out_dtype)
 

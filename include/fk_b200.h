@@ -152,6 +152,16 @@ int fk_attn_forward_tc(const void* q, const void* k, const void* vt, int Sp, voi
                        long long o_ts, const int* qid, const int* kid, const int* qmin, const int* qmax, const int* kmin,
                        const int* kmax, float scale, void* stream);
 
+/* Fused residual add + norm on the fp32 residual stream: x_out = x + delta (bf16), y = norm(x_out)
+ * (the pair `x = x + branch(...)`; `ln(x)` of models/brainformer.py:243-244).  Backward: dx = norm_backward(g_y) + g_res
+ * (g_res nullable = gradient reaching x_out through the residual path), written as fp32 and, if dx_bf16 != NULL, as a
+ * bf16 copy for the delta branch.  y / g_y dtype codes as fk_norm_forward. */
+int fk_add_norm_forward(const float* x, const void* delta_bf16, const float* weight, const float* bias, float* x_out,
+                        void* y, int y_dtype, float* mean, float* rstd, long long M, int D, float eps, int rms, void* stream);
+int fk_add_norm_backward(const float* x_new, const void* g_y, int g_dtype, const float* g_res, const float* weight,
+                         const float* mean, const float* rstd, float* dx, void* dx_bf16, float* dw_part, float* db_part,
+                         long long M, int D, int rms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

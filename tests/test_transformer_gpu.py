@@ -196,3 +196,30 @@ def _unused_param_counts():
     assert tuple(enc.attn_mask.shape) == (6144, 6144)
     full = bf.BrainFormer(bf.Config(encoder=mc, n_output_tokens=32, output_dim=768))
     assert round(full.get_num_params() / 1e6, 2) == 6.32
+
+
+@pytest.mark.parametrize("out_dt", [torch.bfloat16, torch.float32])
+def test_add_layer_norm_fwd_bwd(out_dt):
+    """fused residual add + LayerNorm == torch add followed by F.layer_norm, including both gradient paths."""
+    from frankenstein_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    M, D = 300, 512
+    x = torch.randn(M, D, generator=g) * 2
+    dl = torch.randn(M, D, generator=g).to(torch.bfloat16)
+    w, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    gy, gx = torch.randn(M, D, generator=g), torch.randn(M, D, generator=g)
+    xd, dd = x.cuda().requires_grad_(True), dl.cuda().requires_grad_(True)
+    wd, bd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    xn, y = ops.add_layer_norm(xd, dd * 1.0, wd, bd, 1e-5, out_dt)
+    ((y.float() * gy.cuda()).sum() + (xn * gx.cuda()).sum()).backward()
+    xr, dr = x.clone().requires_grad_(True), dl.float().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    xnr = xr + dr
+    yr = F.layer_norm(xnr, (D,), wr, br, 1e-5)
+    ((yr * gy).sum() + (xnr * gx).sum()).backward()
+    close(xn, xnr, rtol=1e-5, what="x_new")
+    close(y, yr, what="y")
+    close(xd.grad, xr.grad, what="dx")
+    close(dd.grad, dr.grad, what="d delta")
+    close(wd.grad, wr.grad, what="dw")
+    close(bd.grad, br.grad, what="db")
