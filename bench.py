@@ -35,7 +35,11 @@ T_BINS, N_CH = 512, 512
 VQ_K, VQ_D, VQ_C = 8192, 256, 256
 CPU_SAMPLE_TRIALS = 2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {"vq_search": 12660480}
+# (attention rows: the capture in profiles/r01_attention_tc_ncu_full.txt is a 16-trial launch; trials are independent,
+#  so a B-trial launch moves B/16 times those bytes)
+NCU_TRAFFIC = {"vq_search": 12659712}
+NCU_TRAFFIC_PER_16_TRIALS = {"attn_fwd": 201787904 + 55185408, "attn_bwd_dkv": 411350528 + 119061248,
+                             "attn_bwd_dq": 344237568 + 60145664}
 
 
 def model_configs():
@@ -317,6 +321,7 @@ def main():
                  "attn_bwd_dq": "fk::attn_bwd_tc_kernel<DQ> (label-mask flash attention dQ, tcgen05/TMEM/TMA)"}
         # ncu --set full captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
         traffic = {"vq_search": NCU_TRAFFIC.get("vq_search")}
+        traffic.update({k: int(v * B / 16) for k, v in NCU_TRAFFIC_PER_16_TRIALS.items()})
         kern = {}
         for name, flops in alg.items():
             if name not in ksum:
