@@ -44,6 +44,7 @@ struct SearchParams {
   int* cand_idx;        // [N][S][kCand] code indices, -1 = none
   uint32_t tag_mask;    // low mantissa bits that carry the tile tag
   float* dbg_scores;    // optional [N][T*kBN] raw accumulators (tests only)
+  long long* prof;      // optional [grid][16] stall counters in cycles (kProf instantiation only)
   long long N;
   int K, nslab, T, RB, S, nstage;
   float alpha;
@@ -92,6 +93,24 @@ __device__ __forceinline__ void scan16(const uint32_t (&r)[16], const float* c2s
   }
 }
 
+// Stall accounting for the profiling instantiation: cycles spent inside a barrier wait are added to `acc`.
+template <bool kProf>
+__device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t phase, long long& acc) {
+  if constexpr (kProf) {
+    // only waits that were NOT already satisfied are charged (count in the high 24 bits, cycles below)
+    if (mbar_test_wait(bar, phase)) return;
+    const long long t = clock64();
+    mbar_wait(bar, phase);
+    acc += (clock64() - t) + (1ll << 40);
+  } else {
+    mbar_wait(bar, phase);
+  }
+}
+
+// prof[cta][32]: 16+h issuer wait+fence+descriptor cycles, 18+h MMA issue cycles, 20+h commit cycles; 0 total, 1 setup, 2 producer wait empty, 3 producer wait x_empty, 4+h issuer wait x_full,
+// 6+h issuer wait tmem_empty, 8+h issuer wait full, 10+h issuer loop total, 12 epilogue(warp 4) wait tmem_full,
+// 13 epilogue flush, 14 epilogue named-barrier wait, 15 first accumulator ready (since start)
+template <bool kProf>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_c,
                  const SearchParams p) {
@@ -112,6 +131,8 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(x_full + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_start = kProf ? clock64() : 0;
+  long long* prof = kProf ? p.prof + static_cast<long long>(blockIdx.x) * 32 : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -138,6 +159,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (kProf && threadIdx.x == 0) prof[1] = clock64() - t_start;
 
   // contiguous range of work units for this CTA
   const long long W = static_cast<long long>(p.RB) * p.T;
@@ -150,15 +172,16 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, seg = 0;
+      long long w_empty = 0, w_xempty = 0;
       for (long long u = u_begin; u < u_end; ++seg) {
         const int rb = static_cast<int>(u / p.T), t0 = static_cast<int>(u % p.T);
         const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
-        mbar_wait(x_empty, (seg & 1) ^ 1);
+        wait_acc<kProf>(x_empty, (seg & 1) ^ 1, w_xempty);
         mbar_expect_tx(x_full, p.nslab * kXSlabBytes);
         for (int ks = 0; ks < p.nslab; ++ks) tma_load_2d(Xs + ks * kXSlabBytes, &tmap_x, x_full, ks * kSlabK, rb * kBM);
         for (int t = t0; t < t0 + nt; ++t) {
           for (int ks = 0; ks < p.nslab; ++ks) {
-            mbar_wait(&empty[stage], phase ^ 1);
+            wait_acc<kProf>(&empty[stage], phase ^ 1, w_empty);
             mbar_expect_tx(&full[stage], kBSlabBytes);
             tma_load_2d(Bs + stage * kBSlabBytes, &tmap_c, &full[stage], ks * kSlabK, t * kBN);
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -166,44 +189,63 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         u += nt;
       }
+      if (kProf) { prof[2] = w_empty; prof[3] = w_xempty; }
     }
   } else if (warp == 1 || warp == 3) {
     // ================================ MMA issuers ================================
     // Two issuing threads, one per accumulator half (rows 0-127 / 128-255): measured on B200 one thread sustains
     // one tcgen05.mma per ~100 cycles while the tensor core accepts an M128 x N128 x K16 MMA every 64
     // (scripts/microbench/umma_rate.cu), so a single issuer caps the kernel at ~60 % of the MMA rate.
-    if (lane == 0) {
-      const int h = (warp == 1) ? 0 : 1;
+    // The WHOLE warp runs this loop (barrier waits by all lanes, one elected lane issues): with warp-uniform control
+    // flow and operands ptxas keeps the descriptors in uniform registers and emits bare UTCHMMA instructions.  A
+    // `lane == 0` branch around the loop made every MMA a divergence "waterfall" (ELECT + 5x R2UR.BROADCAST + branch,
+    // ~115 cycles per issue; scripts/gpu_search_stalls.py).
+    {
+      const int h = (__shfl_sync(0xffffffffu, warp, 0) == 1) ? 0 : 1;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc = umma_idesc_bf16(128, kBN);
       const uint32_t xs_addr = smem_u32(Xs) + h * (128 * 128), bs_addr = smem_u32(Bs);
       int stage = 0;
       uint32_t phase = 0, seg = 0, tc = 0;
+      long long w_x = 0, w_te = 0, w_full = 0, c_pre = 0, c_mma = 0, c_commit = 0;
+      const long long t_loop = kProf ? clock64() : 0;
       for (long long u = u_begin; u < u_end; ++seg) {
         const int t0 = static_cast<int>(u % p.T);
         const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
-        mbar_wait(x_full, seg & 1);
+        wait_acc<kProf>(x_full, seg & 1, w_x);
         tc_fence_after();
         for (int t = 0; t < nt; ++t, ++tc) {
           const uint32_t as = tc & 1;
-          mbar_wait(&tmem_empty[as * 2 + h], ((tc >> 1) & 1) ^ 1);
+          wait_acc<kProf>(&tmem_empty[as * 2 + h], ((tc >> 1) & 1) ^ 1, w_te);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (h * 2 + as) * kBN;
+          const uint32_t d_tmem = tmem_u + (h * 2 + as) * kBN;
           for (int ks = 0; ks < p.nslab; ++ks) {
-            mbar_wait(&full[stage], phase);
+            const long long c0 = kProf ? clock64() : 0;
+            wait_acc<kProf>(&full[stage], phase, w_full);
             tc_fence_after();
             const uint64_t adesc = umma_desc_sw128(xs_addr + ks * kXSlabBytes);
             const uint64_t bdesc = umma_desc_sw128(bs_addr + stage * kBSlabBytes);
+            const long long c1 = kProf ? clock64() : 0;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)      // a K step of 16 bf16 = 32 bytes = +2 in the (address >> 4) field
-              umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (ks | kk) != 0);
-            umma_commit(&empty[stage]);   // slab free once the MMAs of both halves have retired (2 arrivals)
+              for (int kk = 0; kk < 4; ++kk)      // a K step of 16 bf16 = 32 bytes = +2 in the (address >> 4) field
+                umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (ks | kk) != 0);
+            }
+            const long long c2 = kProf ? clock64() : 0;
+            if (elect_one()) umma_commit(&empty[stage]);   // slab free once the MMAs of both halves have retired (2 arrivals)
+            __syncwarp();
+            if (kProf) { const long long c3 = clock64(); c_pre += c1 - c0; c_mma += c2 - c1; c_commit += c3 - c2; }
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full[as * 2 + h]);
+          if (elect_one()) umma_commit(&tmem_full[as * 2 + h]);
+          __syncwarp();
         }
-        umma_commit(x_empty);
+        if (elect_one()) umma_commit(x_empty);
+        __syncwarp();
         u += nt;
       }
+      if (kProf && lane == 0) { prof[4 + h] = w_x; prof[6 + h] = w_te; prof[8 + h] = w_full; prof[10 + h] = clock64() - t_loop;
+                   prof[16 + h] = c_pre; prof[18 + h] = c_mma; prof[20 + h] = c_commit; }
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
@@ -222,6 +264,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (etid < kBN && u_begin < u_end) c2s[etid] = __ldg(p.c2pad + (u_begin % p.T) * kBN + etid);
     named_bar_sync(1, kEpilogueThreads);
     uint32_t tc = 0;
+    long long w_tf = 0, w_flush = 0, w_bar = 0;
     int t_seg0 = static_cast<int>(u_begin % p.T);        // first tile of the current segment
     for (long long u = u_begin; u < u_end; ++u, ++tc) {
       const int rb = static_cast<int>(u / p.T), t = static_cast<int>(u % p.T);
@@ -231,7 +274,8 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (have_next) c2_next = __ldg(p.c2pad + ((u + 1) % p.T) * kBN + etid);
       const float* my_c2 = c2s + as * kBN + cpart * 64;
       const uint32_t tag = static_cast<uint32_t>(t - t_seg0) * 2u;
-      mbar_wait(&tmem_full[as * 2 + h], (tc >> 1) & 1);
+      wait_acc<kProf>(&tmem_full[as * 2 + h], (tc >> 1) & 1, w_tf);
+      if (kProf && tc == 0 && warp == 4 && lane == 0) prof[15] = clock64() - t_start;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (h * 2 + as) * kBN + cpart * 64;
       const long long row = static_cast<long long>(rb) * kBM + h * 128 + q * 32 + lane;
@@ -256,7 +300,10 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (lane == 0) mbar_arrive(&tmem_empty[as * 2 + h]);
       scan16(rb2, my_c2 + 48, p.alpha, keep_mask, tag + 1u, m, 16, dbg ? dbg + 48 : nullptr);
       if (have_next) c2s[(as ^ 1) * kBN + etid] = c2_next;
+      const long long t_bar = kProf ? clock64() : 0;
       named_bar_sync(1, kEpilogueThreads);      // c2 of the next tile visible; this tile's c2 reads finished
+      if (kProf) w_bar += clock64() - t_bar;
+      const long long t_flush = kProf ? clock64() : 0;
       if (t == p.T - 1 || u + 1 == u_end) {
         // ---- end of a segment: the kCand smallest class keys of this (row, cpart) -> its candidate slot ----
         float cv[kCand];
@@ -290,8 +337,10 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) m[i] = inf;
         t_seg0 = 0;                                   // the next segment starts a new row block at tile 0
+        if (kProf) w_flush += clock64() - t_flush;
       }
     }
+    if (kProf && warp == 4 && lane == 0) { prof[12] = w_tf; prof[13] = w_flush; prof[14] = w_bar; }
   }
 
   tc_fence_before();
@@ -300,6 +349,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (kProf && threadIdx.x == 0) prof[0] = clock64() - t_start;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -333,18 +383,31 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_search_slots(long lo
   return 2 * S;   // two column halves per segment
 }
 
-extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
-                                  int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, float* dbg_scores,
-                                  void* stream_);
+static int search_launch(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                         int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, float* dbg_scores,
+                         long long* prof, void* stream_);
 
 extern "C" __attribute__((visibility("default"))) int fk_vq_search(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
                             int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, void* stream_) {
-  return fk_vq_search_debug(x_bf16, cb_bf16, c2pad, N, K, Dp, use_cosine, cand_val, cand_idx, S, max_ctas, nullptr, stream_);
+  return search_launch(x_bf16, cb_bf16, c2pad, N, K, Dp, use_cosine, cand_val, cand_idx, S, max_ctas, nullptr, nullptr, stream_);
 }
 
 extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
                                   int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, float* dbg_scores,
                                   void* stream_) {
+  return search_launch(x_bf16, cb_bf16, c2pad, N, K, Dp, use_cosine, cand_val, cand_idx, S, max_ctas, dbg_scores, nullptr, stream_);
+}
+
+extern "C" __attribute__((visibility("default"))) int fk_vq_search_profile(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                                    int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, long long* prof,
+                                    void* stream_) {
+  FK_REQUIRE(prof != nullptr, "fk_vq_search_profile: null counter buffer");
+  return search_launch(x_bf16, cb_bf16, c2pad, N, K, Dp, use_cosine, cand_val, cand_idx, S, max_ctas, nullptr, prof, stream_);
+}
+
+static int search_launch(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                         int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, float* dbg_scores,
+                         long long* prof, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(N > 0 && K > 0, "fk_vq_search: empty problem");
   FK_REQUIRE(Dp % 64 == 0 && Dp >= 64 && Dp <= 256, "fk_vq_search: padded dim must be 64, 128, 192 or 256");
@@ -366,6 +429,7 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const v
   p.cand_val = cand_val;
   p.cand_idx = cand_idx;
   p.dbg_scores = dbg_scores;
+  p.prof = prof;
   p.N = N;
   p.K = K;
   p.nslab = Dp / 64;
@@ -387,7 +451,8 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const v
 
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(vq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess) {
+    if (cudaFuncSetAttribute(vq_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
+        cudaFuncSetAttribute(vq_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess) {
       fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
       return FK_ERR_CUDA;
     }
@@ -395,7 +460,10 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_search_debug(const v
   }
   // unused slots must read as "no candidate"
   if (cudaMemsetAsync(cand_idx, 0xFF, static_cast<size_t>(N) * S * kCand * sizeof(int), stream) != cudaSuccess) return FK_ERR_CUDA;
-  vq_search_kernel<<<static_cast<unsigned>(G), kSearchThreads, smem_bytes, stream>>>(tx, tcm, p);
+  if (prof != nullptr)
+    vq_search_kernel<true><<<static_cast<unsigned>(G), kSearchThreads, smem_bytes, stream>>>(tx, tcm, p);
+  else
+    vq_search_kernel<false><<<static_cast<unsigned>(G), kSearchThreads, smem_bytes, stream>>>(tx, tcm, p);
   FK_CHECK_LAUNCH();
   fk_count_launch(2);
   return FK_OK;

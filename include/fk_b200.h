@@ -50,6 +50,12 @@ int fk_vq_search_debug(const void* x_bf16, const void* cb_bf16, const float* c2p
                        int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, float* dbg_scores,
                        void* stream);
 
+/* Same kernel built with stall accounting (performance diagnosis only; scripts/gpu_search_stalls.py): prof is
+ * int64 [n_ctas, 32] cycle counters (total, setup, producer / issuer / epilogue barrier waits; see vq_search.cu). */
+int fk_vq_search_profile(const void* x_bf16, const void* cb_bf16, const float* c2pad, long long N, int K, int Dp,
+                         int use_cosine, float* cand_val, int* cand_idx, int S, int max_ctas, long long* prof,
+                         void* stream);
+
 /* ---- VQ: exact re-score + gather + straight-through + commitment loss ------------------------ */
 /* Replaces gumbel_sample(argmax), `quantize = onehot @ embed`, `x + (quantize - x).detach()` and
  * `F.mse_loss(quantize.detach(), x) * commitment_weight` (VectorQuantize.forward).

@@ -24,7 +24,7 @@ def time_fn(fn, iters=20, warm=5):
 
 
 def main():
-    shapes = [(4096, 512, 64), (16384, 8192, 256), (16384, 512, 256), (16384, 2048, 256), (16384, 32768, 256), (16384, 65536, 256)]
+    shapes = [(4096, 512, 64)] + [(16384, k, 256) for k in (512, 1024, 2048, 4096, 8192, 16384, 32768, 65536)]
     if "--shape" in sys.argv:
         i = sys.argv.index("--shape")
         shapes = [tuple(int(v) for v in sys.argv[i + 1:i + 4])]
