@@ -43,7 +43,27 @@ struct TcParams {
   long long o0_bs, o0_ts, o1_bs, o1_ts;
   int B, H, S_row, S_col, Sq;
   float scale, scale_log2;
+  long long* prof;                                     // kProf instantiation: [n_ctas][16] cycle counters
 };
+
+// Diagnosis only (scripts/gpu_attn_stalls.py): when a buffer is set, fk_attn_backward_tc launches the stall-accounting
+// instantiation, which writes per CTA: 0 lifetime, 1 setup, 2 tiles, 3 first score stage ready, 4 sum wait sdp_full,
+// 5 sum wait pbuf_free, 6 sum named barrier, 7 sum compute, 8 last p_ready, 9 accumulators complete, 10 stores done,
+// 11 score issuer wait st_full, 12 score issuer wait sdp_free, 13 acc issuer wait p_ready, 14 producer wait st_empty
+// (3..10 by warpgroup 0, warp 4, lane 0; times since CTA start).
+static long long* g_attn_prof = nullptr;
+
+template <bool kProf>
+__device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t phase, long long& acc) {
+  if constexpr (kProf) {
+    if (mbar_test_wait(bar, phase)) return;
+    const long long t = clock64();
+    mbar_wait(bar, phase);
+    acc += clock64() - t;
+  } else {
+    mbar_wait(bar, phase);
+  }
+}
 
 struct TcSmem {
   // offsets from the 1024-aligned dynamic smem base
@@ -111,7 +131,7 @@ __device__ __forceinline__ void tmem_wait1_32(uint32_t (&a)[32]) {
                :: "memory");
 }
 
-template <int MODE>
+template <int MODE, bool kProf>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_constant__ CUtensorMap tm_resB,
                    const __grid_constant__ CUtensorMap tm_stA, const __grid_constant__ CUtensorMap tm_stB,
@@ -134,6 +154,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int r0 = rt * kRows;
+  const long long t_start = kProf ? clock64() : 0;
+  long long* prof = kProf ? p.prof + ((static_cast<long long>(b) * gridDim.y + h) * gridDim.x + rt) * 16 : nullptr;
   const bool masked = p.row_id != nullptr;
   const int n_col_tiles = (p.S_col + kCols - 1) / kCols;
   const int n_row_tiles64 = (p.S_row + 63) / 64;
@@ -199,74 +221,103 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int T = *n_tiles_slot;
+  if (kProf && threadIdx.x == 0) { prof[1] = clock64() - t_start; prof[2] = T; }
 
   constexpr uint32_t kStageBytes = (MODE == MODE_DKV) ? 16384u : 12288u;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      mbar_expect_tx(res_full, 16384);
-      tma_load_4d(smem + TcSmem::resA, &tm_resA, res_full, 0, h, r0, b);
-      tma_load_4d(smem + TcSmem::resB, &tm_resB, res_full, 0, h, r0, b);
+    // Control warps run their loops with the WHOLE warp (uniform control flow; barrier waits by all lanes) and issue
+    // the asynchronous operation from one elected lane: operands then live in uniform registers and ptxas emits bare
+    // UTMALDG / UTCHMMA / UTCBAR instructions.  Under a `lane == 0` branch every such instruction became a divergence
+    // waterfall (ELECT + R2UR.BROADCAST chain + branch, ~115 cycles per MMA issue -- scripts/gpu_search_stalls.py).
+    {
+      const int T_u = __shfl_sync(0xffffffffu, T, 0);
+      if (elect_one()) {
+        mbar_expect_tx(res_full, 16384);
+        tma_load_4d(smem + TcSmem::resA, &tm_resA, res_full, 0, h, r0, b);
+        tma_load_4d(smem + TcSmem::resB, &tm_resB, res_full, 0, h, r0, b);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        const int t = tile_list[j] & 0x7fff;
+      long long w_se = 0;
+      for (int j = 0; j < T_u; ++j) {
+        const int t = __shfl_sync(0xffffffffu, tile_list[j] & 0x7fff, 0);
         uint8_t* st = smem + TcSmem::stream + stage * 16384;
-        mbar_wait(&st_empty[stage], phase ^ 1);
-        mbar_expect_tx(&st_full[stage], kStageBytes);
-        tma_load_4d(st, &tm_stA, &st_full[stage], 0, h, t * kCols, b);
-        tma_load_4d(st + 4096, &tm_stB, &st_full[stage], 0, h, t * kCols, b);
-        if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[stage], t * kCols, (b * p.H + h) * 32);
-        tma_load_2d(st + 12288, &tm_tB, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+        wait_acc<kProf>(&st_empty[stage], phase ^ 1, w_se);
+        if (elect_one()) {
+          mbar_expect_tx(&st_full[stage], kStageBytes);
+          tma_load_4d(st, &tm_stA, &st_full[stage], 0, h, t * kCols, b);
+          tma_load_4d(st + 4096, &tm_stB, &st_full[stage], 0, h, t * kCols, b);
+          if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+          tma_load_2d(st + 12288, &tm_tB, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+        }
+        __syncwarp();
         if (++stage == kNST) { stage = 0; phase ^= 1; }
       }
+      if (kProf && lane == 0) prof[14] = w_se;
     }
   } else if (warp == 1) {
     // ================================ score-MMA issuer ================================
     // (measured on B200: one thread sustains one tcgen05.mma per ~97 cycles and the tensor core accepts one per
     //  ~60 cycles whatever N <= 128 is -- scripts/microbench/umma_rate.cu -- so the score MMAs and the accumulate
     //  MMAs are issued by two different threads.)
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_score = umma_idesc_bf16(kRows, kCols);
+      const int T_u = __shfl_sync(0xffffffffu, T, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t dA = umma_desc_sw64(smem_u32(smem + TcSmem::resA)), dB = umma_desc_sw64(smem_u32(smem + TcSmem::resB));
       const uint32_t stream = smem_u32(smem + TcSmem::stream);
       mbar_wait(res_full, 0);
       tc_fence_after();
-      for (int js = 0; js < T; ++js) {
+      long long w_sf = 0, w_free = 0;
+      for (int js = 0; js < T_u; ++js) {
         const int stage = js % kNST, g = js & 1;
-        mbar_wait(&st_full[stage], (js / kNST) & 1);
-        mbar_wait(&sdp_free[g], ((js >> 1) & 1) ^ 1);
+        wait_acc<kProf>(&st_full[stage], (js / kNST) & 1, w_sf);
+        wait_acc<kProf>(&sdp_free[g], ((js >> 1) & 1) ^ 1, w_free);
         tc_fence_after();
         const uint64_t dS = umma_desc_sw64(stream + stage * 16384), dD = umma_desc_sw64(stream + stage * 16384 + 4096);
-        // a K step of 16 bf16 = 32 bytes = +2 in the descriptor's (address >> 4) field
-        umma_bf16(tmem_base + g * 128, dA, dS, idesc_score, 0u);
-        umma_bf16(tmem_base + g * 128, dA + 2, dS + 2, idesc_score, 1u);
-        umma_bf16(tmem_base + g * 128 + 64, dB, dD, idesc_score, 0u);
-        umma_bf16(tmem_base + g * 128 + 64, dB + 2, dD + 2, idesc_score, 1u);
-        umma_commit(&sdp_full[g]);
+        if (elect_one()) {
+          // a K step of 16 bf16 = 32 bytes = +2 in the descriptor's (address >> 4) field
+          umma_bf16(tmem_u + g * 128, dA, dS, idesc_score, 0u);
+          umma_bf16(tmem_u + g * 128, dA + 2, dS + 2, idesc_score, 1u);
+          umma_bf16(tmem_u + g * 128 + 64, dB, dD, idesc_score, 0u);
+          umma_bf16(tmem_u + g * 128 + 64, dB + 2, dD + 2, idesc_score, 1u);
+          umma_commit(&sdp_full[g]);
+        }
+        __syncwarp();
       }
+      if (kProf && lane == 0) { prof[11] = w_sf; prof[12] = w_free; }
     }
   } else if (warp == 3) {
     // ================================ accumulate-MMA issuer ================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_acc = umma_idesc_bf16(kRows, 32);
+      const int T_u = __shfl_sync(0xffffffffu, T, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t stream = smem_u32(smem + TcSmem::stream);
-      for (int ia = 0; ia < T; ++ia) {
+      long long w_pr = 0;
+      for (int ia = 0; ia < T_u; ++ia) {
         const int stage = ia % kNST, pb = ia % kNP;
-        mbar_wait(&p_ready[pb], (ia / kNP) & 1);
+        wait_acc<kProf>(&p_ready[pb], (ia / kNP) & 1, w_pr);
         tc_fence_after();
         const uint64_t dTA = umma_desc_sw128(stream + stage * 16384 + 8192), dTB = umma_desc_sw128(stream + stage * 16384 + 12288);
-        const uint32_t ta = tmem_base + 256 + pb * 64;       // P at +0..31, dS at +32..63 (bf16 pairs)
+        const uint32_t ta = tmem_u + 256 + pb * 64;       // P at +0..31, dS at +32..63 (bf16 pairs)
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if (MODE == MODE_DKV) umma_bf16_ts(tmem_base + 448, ta + kk * 8, dTA + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
-          umma_bf16_ts(tmem_base + 480, ta + 32 + kk * 8, dTB + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {
+            if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + 448, ta + kk * 8, dTA + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16_ts(tmem_u + 480, ta + 32 + kk * 8, dTB + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&pbuf_free[pb]);
+          umma_commit(&st_empty[stage]);
         }
-        umma_commit(&pbuf_free[pb]);
-        umma_commit(&st_empty[stage]);
+        __syncwarp();
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
+      if (kProf && lane == 0) prof[13] = w_pr;
     }
   } else if (warp >= 4) {
     // ================================ compute warpgroups ================================
@@ -304,6 +355,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       }
     };
     prefetch(g);
+    long long w_full = 0, w_pb = 0, w_bar = 0, w_comp = 0;
+    const bool prof_me = kProf && warp == 4 && lane == 0;
     for (int j = g; j < T; j += 2) {
       const bool need_mask = (tile_list[j] & 0x8000) != 0;
       // column statistics: double buffered per warpgroup, so one barrier per tile (write -> barrier -> read; the
@@ -316,11 +369,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       } else if (tid < 64) {
         s_id[tid] = pre_i;
       }
+      const long long tb0 = kProf ? clock64() : 0;
       named_bar_sync(1 + g, 128);
+      if (kProf) w_bar += clock64() - tb0;
       prefetch(j + 2);
       const int n = j >> 1, pb = j % kNP;
-      mbar_wait(&sdp_full[g], n & 1);
-      mbar_wait(&pbuf_free[pb], ((j / kNP) & 1) ^ 1);      // operand buffer pb no longer read by older MMAs
+      wait_acc<kProf>(&sdp_full[g], n & 1, w_full);
+      if (prof_me && j == 0) prof[3] = clock64() - t_start;
+      wait_acc<kProf>(&pbuf_free[pb], ((j / kNP) & 1) ^ 1, w_pb);      // operand buffer pb no longer read by older MMAs
+      const long long tc0 = kProf ? clock64() : 0;
       tc_fence_after();
       const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
       const uint32_t taddr = tmem_base + lane_base + g * 128;
@@ -385,9 +442,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[pb]);
+      if (kProf) w_comp += clock64() - tc0;
     }
+    if (prof_me) { prof[4] = w_full; prof[5] = w_pb; prof[6] = w_bar; prof[7] = w_comp; prof[8] = clock64() - t_start; }
     // ---- epilogue: accumulators -> bf16 -> global ----
     mbar_wait(acc_full, 0);
+    if (prof_me) prof[9] = clock64() - t_start;
     tc_fence_after();
     const bool writes = (MODE == MODE_DKV) || (g == 1);     // warp-uniform
     if (writes) {
@@ -419,6 +479,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         }
       }
     }
+    if (prof_me) prof[10] = clock64() - t_start;
   }
 
   tc_fence_before();
@@ -427,6 +488,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (kProf && threadIdx.x == 0) prof[0] = clock64() - t_start;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -580,32 +642,42 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 16384);
-      tma_load_4d(smem + FwdSmem::q, &tm_q, q_full, 0, h, q0, b);
-      tma_load_4d(smem + FwdSmem::q + 8192, &tm_q, q_full, 0, h, q0 + 128, b);
+    // (whole-warp loops with one elected issuing lane: see the backward kernel)
+    {
+      const int T_u = __shfl_sync(0xffffffffu, T, 0);
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 16384);
+        tma_load_4d(smem + FwdSmem::q, &tm_q, q_full, 0, h, q0, b);
+        tma_load_4d(smem + FwdSmem::q + 8192, &tm_q, q_full, 0, h, q0 + 128, b);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        const int t = tile_list[j] & 0x3fff;
+      for (int j = 0; j < T_u; ++j) {
+        const int t = __shfl_sync(0xffffffffu, tile_list[j] & 0x3fff, 0);
         uint8_t* st = smem + FwdSmem::stream + stage * 16384;
         mbar_wait(&st_empty[stage], phase ^ 1);
-        mbar_expect_tx(&st_full[stage], 16384);
-        tma_load_4d(st, &tm_k, &st_full[stage], 0, h, t * kFwdTileK, b);
-        tma_load_2d(st + 8192, &tm_vt, &st_full[stage], t * kFwdTileK, (b * p.H + h) * 32);
-        tma_load_2d(st + 12288, &tm_vt, &st_full[stage], t * kFwdTileK + 64, (b * p.H + h) * 32);
+        if (elect_one()) {
+          mbar_expect_tx(&st_full[stage], 16384);
+          tma_load_4d(st, &tm_k, &st_full[stage], 0, h, t * kFwdTileK, b);
+          tma_load_2d(st + 8192, &tm_vt, &st_full[stage], t * kFwdTileK, (b * p.H + h) * 32);
+          tma_load_2d(st + 12288, &tm_vt, &st_full[stage], t * kFwdTileK + 64, (b * p.H + h) * 32);
+        }
+        __syncwarp();
         if (++stage == kNST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================ score-MMA issuer ================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, kFwdTileK);
+      const int T_u = __shfl_sync(0xffffffffu, T, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t dQ[2] = {umma_desc_sw64(smem_u32(smem + FwdSmem::q)), umma_desc_sw64(smem_u32(smem + FwdSmem::q + 8192))};
       const uint32_t stream = smem_u32(smem + FwdSmem::stream);
       mbar_wait(q_full, 0);
       tc_fence_after();
-      for (int j = 0; j < T; ++j) {
+      for (int j = 0; j < T_u; ++j) {
         const int stage = j % kNST;
         mbar_wait(&st_full[stage], (j / kNST) & 1);
         const uint64_t dK = umma_desc_sw64(stream + stage * 16384);
@@ -613,30 +685,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int g = 0; g < 2; ++g) {
           mbar_wait(&s_free[g], (j & 1) ^ 1);
           tc_fence_after();
-          umma_bf16(tmem_base + g * 128, dQ[g], dK, idesc, 0u);
-          umma_bf16(tmem_base + g * 128, dQ[g] + 2, dK + 2, idesc, 1u);
-          umma_commit(&s_full[g]);
+          if (elect_one()) {
+            umma_bf16(tmem_u + g * 128, dQ[g], dK, idesc, 0u);
+            umma_bf16(tmem_u + g * 128, dQ[g] + 2, dK + 2, idesc, 1u);
+            umma_commit(&s_full[g]);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 3) {
     // ================================ P V MMA issuer ================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
+      const int T_u = __shfl_sync(0xffffffffu, T, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t stream = smem_u32(smem + FwdSmem::stream);
-      for (int j = 0; j < T; ++j) {
+      for (int j = 0; j < T_u; ++j) {
         const int stage = j % kNST;
         const uint64_t dV0 = umma_desc_sw128(stream + stage * 16384 + 8192), dV1 = umma_desc_sw128(stream + stage * 16384 + 12288);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           mbar_wait(&p_ready[g], j & 1);
           tc_fence_after();
-          const uint32_t pa = tmem_base + 256 + g * 64, oa = tmem_base + 384 + g * 32;
+          const uint32_t pa = tmem_u + 256 + g * 64, oa = tmem_u + 384 + g * 32;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16_ts(oa, pa + kk * 8, (kk < 4 ? dV0 : dV1) + 2 * (kk & 3), idesc, (j > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(&p_free[g]);
-          umma_commit(&st_empty[stage]);
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_ts(oa, pa + kk * 8, (kk < 4 ? dV0 : dV1) + 2 * (kk & 3), idesc, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&p_free[g]);
+            umma_commit(&st_empty[stage]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -797,6 +877,12 @@ FK_API int fk_attn_transpose(const void* x, long long bs, long long ts, int B, i
   return FK_OK;
 }
 
+// Diagnosis only: route fk_attn_backward_tc to the stall-accounting instantiation (prof: int64 [n_ctas, 16]; null = off).
+FK_API int fk_attn_set_profile_buffer(long long* prof) {
+  g_attn_prof = prof;
+  return FK_OK;
+}
+
 // parts: 2 = dK/dV (needs qt, dot), 4 = dQ (needs kt).  delta must already hold rowsum(dO * O) (fk_attn_backward parts=1).
 FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
                                const void* dot, int Sp, const float* lse, const float* delta, void* dq, void* dk, void* dv,
@@ -815,8 +901,10 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
   FK_REQUIRE(Sp >= S && Sp % 8 == 0, "fk_attn_backward_tc: Sp must be >= S and a multiple of 8");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess) {
       fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
       return FK_ERR_CUDA;
     }
@@ -852,7 +940,9 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.out0 = static_cast<__nv_bfloat16*>(dv); p.o0_bs = dv_bs; p.o0_ts = dv_ts;
     p.out1 = static_cast<__nv_bfloat16*>(dk); p.o1_bs = dk_bs; p.o1_ts = dk_ts;
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-    attn_bwd_tc_kernel<MODE_DKV><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
+    p.prof = g_attn_prof;
+    if (g_attn_prof) attn_bwd_tc_kernel<MODE_DKV, true><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
+    else attn_bwd_tc_kernel<MODE_DKV, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
     FK_CHECK_LAUNCH();
     ++n;
   }
@@ -862,7 +952,9 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.lse = lse; p.delta = delta;
     p.out0 = nullptr; p.out1 = static_cast<__nv_bfloat16*>(dq); p.o1_bs = dq_bs; p.o1_ts = dq_ts;
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-    attn_bwd_tc_kernel<MODE_DQ><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
+    p.prof = g_attn_prof;
+    if (g_attn_prof) attn_bwd_tc_kernel<MODE_DQ, true><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
+    else attn_bwd_tc_kernel<MODE_DQ, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
     FK_CHECK_LAUNCH();
     ++n;
   }

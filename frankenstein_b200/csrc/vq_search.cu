@@ -169,7 +169,8 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // (whole warp runs the loop, one elected lane issues -- see the MMA issuers below)
+    {
       int stage = 0;
       uint32_t phase = 0, seg = 0;
       long long w_empty = 0, w_xempty = 0;
@@ -177,19 +178,25 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int rb = static_cast<int>(u / p.T), t0 = static_cast<int>(u % p.T);
         const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
         wait_acc<kProf>(x_empty, (seg & 1) ^ 1, w_xempty);
-        mbar_expect_tx(x_full, p.nslab * kXSlabBytes);
-        for (int ks = 0; ks < p.nslab; ++ks) tma_load_2d(Xs + ks * kXSlabBytes, &tmap_x, x_full, ks * kSlabK, rb * kBM);
+        if (elect_one()) {
+          mbar_expect_tx(x_full, p.nslab * kXSlabBytes);
+          for (int ks = 0; ks < p.nslab; ++ks) tma_load_2d(Xs + ks * kXSlabBytes, &tmap_x, x_full, ks * kSlabK, rb * kBM);
+        }
+        __syncwarp();
         for (int t = t0; t < t0 + nt; ++t) {
           for (int ks = 0; ks < p.nslab; ++ks) {
             wait_acc<kProf>(&empty[stage], phase ^ 1, w_empty);
-            mbar_expect_tx(&full[stage], kBSlabBytes);
-            tma_load_2d(Bs + stage * kBSlabBytes, &tmap_c, &full[stage], ks * kSlabK, t * kBN);
+            if (elect_one()) {
+              mbar_expect_tx(&full[stage], kBSlabBytes);
+              tma_load_2d(Bs + stage * kBSlabBytes, &tmap_c, &full[stage], ks * kSlabK, t * kBN);
+            }
+            __syncwarp();
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
           }
         }
         u += nt;
       }
-      if (kProf) { prof[2] = w_empty; prof[3] = w_xempty; }
+      if (kProf && lane == 0) { prof[2] = w_empty; prof[3] = w_xempty; }
     }
   } else if (warp == 1 || warp == 3) {
     // ================================ MMA issuers ================================

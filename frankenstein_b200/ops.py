@@ -243,6 +243,9 @@ def _rope_inplace(x4, spec: RopeSpec, inverse: bool):
 # ------------------------------------------------------------------------------------------------
 # attention on the fused QKV projection
 # ------------------------------------------------------------------------------------------------
+_BWD_PARTS = (2, 4)     # diagnosis hook (scripts/gpu_attn_stalls.py profiles one backward kernel at a time)
+
+
 class _AttnQKVFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, n_heads, rope, mask, scale):
@@ -325,6 +328,8 @@ class _AttnQKVFn(torch.autograd.Function):
                           "fk_attn_transpose")
                     tr[name] = t
             for name, part in (("attn_bwd_dkv", 2), ("attn_bwd_dq", 4)):
+                if part not in _BWD_PARTS:
+                    continue
                 with timed(name):
                     check(lib().fk_attn_backward_tc(ptr(q), ptr(k), ptr(v), ptr(d4), ptr(tr["q"]), ptr(tr["k"]), ptr(tr["do"]), Sp,
                                                     ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv), B, H, S, hd,

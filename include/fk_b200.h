@@ -138,6 +138,10 @@ int fk_attn_backward(const void* q, const void* k, const void* v, const void* o,
                      long long dk_bs, long long dk_ts, long long dv_bs, long long dv_ts, const int* qid, const int* kid,
                      const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, int parts, void* stream);
 
+/* Diagnosis only (scripts/gpu_attn_stalls.py): while a buffer is set, fk_attn_backward_tc launches a stall-accounting
+ * build of the same kernel that writes int64 [n_ctas, 16] cycle counters (see attention_tc.cu); null switches it off. */
+int fk_attn_set_profile_buffer(long long* prof);
+
 /* tcgen05 / TMEM / TMA version of the attention backward (attention_tc.cu).  fk_attn_transpose makes the
  * [B][H][32][Sp] copies (zero padded, Sp % 8 == 0) that serve as K-major operands for contractions over tokens:
  * qt, dot for dK/dV (parts & 2), kt for dQ (parts & 4).  delta must already hold rowsum(dO*O)

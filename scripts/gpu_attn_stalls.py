@@ -1,0 +1,46 @@
+"""Where do the tcgen05 attention-backward CTAs spend their cycles?  Runs fk_attn_backward_tc with the stall-accounting
+instantiation (fk_attn_set_profile_buffer) at the cfg-2 shape and prints per-CTA means.  Diagnosis only."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from frankenstein_b200 import ops
+from frankenstein_b200._lib import lib, ptr, check
+
+NAMES = ["lifetime", "setup", "tiles", "first_scores_ready@", "wg0_wait_sdp_full", "wg0_wait_pbuf_free", "wg0_named_barrier",
+         "wg0_compute", "wg0_last_p_ready@", "acc_complete@", "stores_done@", "score_iss_wait_st_full",
+         "score_iss_wait_sdp_free", "acc_iss_wait_p_ready", "producer_wait_st_empty", "-"]
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    S, H = 4096, 16
+    dev = torch.device("cuda")
+    qkv = torch.randn(B, S, 3 * H * 32, device=dev, dtype=torch.bfloat16)
+    mask = ops.LabelMask.block_causal(B, S, 256, dev)
+    w = torch.randn(B, S, H * 32, device=dev, dtype=torch.bfloat16)
+    n_cta = B * H * (S // 128)
+    for parts, name in ((2, "dK/dV kernel"), (4, "dQ kernel")):
+        prof = torch.zeros(n_cta, 16, device=dev, dtype=torch.int64)
+        check(lib().fk_attn_set_profile_buffer(ptr(prof)), "set")
+        ops._BWD_PARTS = (parts,)
+        for _ in range(2):
+            x = qkv.clone().requires_grad_(True)
+            out = ops.attention_qkv(x * 1.0, H, None, mask)
+            out.backward(w)
+        ops._BWD_PARTS = (2, 4)
+        torch.cuda.synchronize()
+        check(lib().fk_attn_set_profile_buffer(None), "unset")
+        p = prof.double().cpu()
+        p = p[p[:, 2] > 0]
+        life = p[:, 0].mean().item()
+        T = p[:, 2].mean().item()
+        print(f"{name}: {p.shape[0]} CTAs, mean tiles {T:.1f}, mean lifetime {life:.0f} cycles = {life / T:.0f} per tile")
+        for i, n in enumerate(NAMES[:15]):
+            print(f"  {n:26s} mean {p[:, i].mean().item():9.0f}  ({100 * p[:, i].mean().item() / life:5.1f} % of lifetime)")
+        steady = (p[:, 8] - p[:, 3]).mean().item()
+        print(f"  steady state (first scores -> last P ready): {steady:.0f} cycles = {steady / T:.0f} per tile; "
+              f"prologue {p[:, 3].mean().item():.0f}, tail {(p[:, 0] - p[:, 8]).mean().item():.0f}")
+
+
+if __name__ == "__main__":
+    main()
