@@ -14,7 +14,8 @@ from typing import Dict, List, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfk_b200.so")
+# FK_LIB_PATH: load an experiment build of the same library (frankenstein_b200.build --variant=...) for kernel diagnosis
+LIB_PATH = os.environ.get("FK_LIB_PATH") or os.path.join(_HERE, "libfk_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fk_b200.h")
 
 _CTYPE = {

@@ -43,7 +43,12 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), variant: str = "") -> str:
+    """Build the library.  ``defines`` / ``variant`` produce an experiment build ``libfk_b200_<variant>.so`` (own object
+    directory) for kernel diagnosis; ``FK_LIB_PATH`` makes ``_lib`` load it.  The default build is the product."""
+    OBJ = os.path.join(CSRC, "build" + ("_" + variant if variant else ""))
+    LIB = os.path.join(HERE, "libfk_b200" + ("_" + variant if variant else "") + ".so")
+    NVCC_FLAGS = list(globals()["NVCC_FLAGS"]) + ["-D" + d for d in defines]
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -73,4 +78,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    _defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    _var = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--variant=")), "")
+    print(build(force="--force" in sys.argv, verbose=True, defines=_defs, variant=_var))

@@ -27,11 +27,15 @@ namespace fk {
 
 constexpr int kRows = 128;        // resident rows per CTA (UMMA M)
 constexpr int kCols = 64;         // streamed tile (UMMA N of the score MMAs, K of the accumulate MMAs)
-constexpr int kNST = 4;           // streamed smem stages
+constexpr int kNST = 8;           // streamed smem stages
 constexpr int kNP = 3;            // TMEM operand buffers for P | dS (bf16 pairs, 64 columns each)
 // TMEM map (512 columns): score stage of warpgroup g at g*128 (S 64 | dP 64); operand buffer b at 256 + b*64
 // (P 32 | dS 32); accumulators at 448 (dV) and 480 (dK / dQ).
-constexpr int kTcThreads = 384;
+constexpr int kNCH = 2;           // column halves of a score tile, one compute warpgroup each (per tile parity)
+constexpr int kColsW = kCols / kNCH;          // score columns per warpgroup
+constexpr int kSub = kColsW / 16;             // 16-column sub-chunks per warpgroup and tile
+constexpr int kGroupThreads = 128 * kNCH;     // compute threads that share a tile
+constexpr int kTcThreads = 128 + 2 * kGroupThreads;
 constexpr int kMaxTiles = 2048;   // streamed tiles per sequence (S <= 131072); entries carry a flag in bit 15
 constexpr int MODE_DKV = 0, MODE_DQ = 1;
 
@@ -52,10 +56,11 @@ struct TcParams {
 // 11 score issuer wait st_full, 12 score issuer wait sdp_free, 13 acc issuer wait p_ready, 14 producer wait st_empty
 // (3..10 by warpgroup 0, warp 4, lane 0; times since CTA start).
 static long long* g_attn_prof = nullptr;
+static int g_attn_prof_mode = 1;   // 1 = full stall accounting, 2 = light (lifetime + global timestamps + SM id)
 
-template <bool kProf>
+template <int kProf>
 __device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t phase, long long& acc) {
-  if constexpr (kProf) {
+  if constexpr (kProf == 1) {
     if (mbar_test_wait(bar, phase)) return;
     const long long t = clock64();
     mbar_wait(bar, phase);
@@ -76,11 +81,21 @@ struct TcSmem {
   static constexpr int total = bars + 256;
 };
 
+// FK_ATTN_EXP (diagnosis builds only, results are WRONG): 1 = no MUFU, 2 = no TMEM operand stores, 3 = no stats LDS,
+// 4 = no math at all between the TMEM loads and stores.
+#ifndef FK_ATTN_EXP
+#define FK_ATTN_EXP 0
+#endif
 __device__ __forceinline__ float fast_ex2(float x) {
+#if FK_ATTN_EXP == 1
+  return x * 0.25f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
+// (F2FP.BF16.PACK_AB runs at full rate, 126 pairs/clk/SM, and MUFU.EX2 at 16/clk/SM: scripts/microbench/xu_rate.cu)
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -122,6 +137,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_wait1_16(uint32_t (&a)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_wait1_32(uint32_t (&a)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
@@ -131,7 +152,7 @@ __device__ __forceinline__ void tmem_wait1_32(uint32_t (&a)[32]) {
                :: "memory");
 }
 
-template <int MODE, bool kProf>
+template <int MODE, int kProf>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_constant__ CUtensorMap tm_resB,
                    const __grid_constant__ CUtensorMap tm_stA, const __grid_constant__ CUtensorMap tm_stB,
@@ -154,8 +175,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int r0 = rt * kRows;
+  constexpr bool kFull = kProf == 1;
   const long long t_start = kProf ? clock64() : 0;
-  long long* prof = kProf ? p.prof + ((static_cast<long long>(b) * gridDim.y + h) * gridDim.x + rt) * 16 : nullptr;
+  unsigned long long g_start = 0;
+  if (kProf == 2 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
+  long long* prof = kProf ? p.prof + ((static_cast<long long>(b) * gridDim.y + h) * gridDim.x + rt) * 24 : nullptr;
   const bool masked = p.row_id != nullptr;
   const int n_col_tiles = (p.S_col + kCols - 1) / kCols;
   const int n_row_tiles64 = (p.S_row + 63) / 64;
@@ -178,10 +202,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     for (int i = 0; i < kNST; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&sdp_free[i], 4);
+      mbar_init(&sdp_free[i], 4 * kNCH);
     }
     for (int i = 0; i < kNP; ++i) {
-      mbar_init(&p_ready[i], 4);
+      mbar_init(&p_ready[i], 4 * kNCH);
       mbar_init(&pbuf_free[i], 1);
     }
     mbar_init(acc_full, 1);
@@ -221,7 +245,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int T = *n_tiles_slot;
-  if (kProf && threadIdx.x == 0) { prof[1] = clock64() - t_start; prof[2] = T; }
+  if (kFull && threadIdx.x == 0) { prof[1] = clock64() - t_start; prof[2] = T; }
 
   constexpr uint32_t kStageBytes = (MODE == MODE_DKV) ? 16384u : 12288u;
 
@@ -256,7 +280,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         __syncwarp();
         if (++stage == kNST) { stage = 0; phase ^= 1; }
       }
-      if (kProf && lane == 0) prof[14] = w_se;
+      if (kFull && lane == 0) prof[14] = w_se;
     }
   } else if (warp == 1) {
     // ================================ score-MMA issuer ================================
@@ -288,7 +312,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         }
         __syncwarp();
       }
-      if (kProf && lane == 0) { prof[11] = w_sf; prof[12] = w_free; }
+      if (kFull && lane == 0) { prof[11] = w_sf; prof[12] = w_free; }
     }
   } else if (warp == 3) {
     // ================================ accumulate-MMA issuer ================================
@@ -317,14 +341,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       }
       if (elect_one()) umma_commit(acc_full);
       __syncwarp();
-      if (kProf && lane == 0) prof[13] = w_pr;
+      if (kFull && lane == 0) prof[13] = w_pr;
     }
   } else if (warp >= 4) {
     // ================================ compute warpgroups ================================
-    const int g = (warp - 4) >> 2;               // warpgroup = tile parity
+    // 2 * kNCH warpgroups: tile parity g x column part ch.  The warpgroups of one parity share a score stage (each
+    // reads its own kColsW columns) so four warps per scheduler keep the MUFU / FMA pipes fed while others wait on TMEM.
+    const int wgi = (warp - 4) >> 2;
+    const int g = wgi & 1;                       // tile parity
+    const int ch = wgi >> 1;                     // column part of the tile
     const int q4 = warp & 3;                     // TMEM lane quarter
     const int r = q4 * 32 + lane;                // resident row owned by this thread
-    const int tid = (warp - 4 - g * 4) * 32 + lane;
+    const int tid = ch * 128 + r;                // index within the parity group
     const int row = r0 + r;
     const bool row_ok = row < p.S_row;
     float* stats_base = reinterpret_cast<float*>(smem + TcSmem::stats) + g * 384;
@@ -340,7 +368,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     float pre_f = 0.f;
     int pre_i = 0;
     auto prefetch = [&](int j) {
-      if (j >= T) return;
+      if (j >= T || tid >= 128) return;
       const int c = (tile_list[j] & 0x7fff) * kCols + (tid & 63);
       const bool ok = c < p.S_col;
       if (MODE == MODE_DKV) {
@@ -355,47 +383,52 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       }
     };
     prefetch(g);
-    long long w_full = 0, w_pb = 0, w_bar = 0, w_comp = 0;
-    const bool prof_me = kProf && warp == 4 && lane == 0;
+    long long w_full = 0, w_pb = 0, w_bar = 0, w_comp = 0, w_ld0 = 0, w_ldn = 0, w_st = 0;
+    const bool prof_me = kFull && warp == 4 && lane == 0;
     for (int j = g; j < T; j += 2) {
       const bool need_mask = (tile_list[j] & 0x8000) != 0;
-      // column statistics: double buffered per warpgroup, so one barrier per tile (write -> barrier -> read; the
+      // column statistics: double buffered per parity group, so one barrier per tile (write -> barrier -> read; the
       // previous tile's readers use the other buffer)
       float* s_lse = stats_base + ((j >> 1) & 1) * 192;
       float* s_delta = s_lse + 64;
       int* s_id = reinterpret_cast<int*>(s_lse + 128);
       if (MODE == MODE_DKV) {
-        if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else { s_delta[tid - 64] = pre_f; }
+        if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else if (tid < 128) { s_delta[tid - 64] = pre_f; }
       } else if (tid < 64) {
         s_id[tid] = pre_i;
       }
-      const long long tb0 = kProf ? clock64() : 0;
-      named_bar_sync(1 + g, 128);
-      if (kProf) w_bar += clock64() - tb0;
+      const long long tb0 = kFull ? clock64() : 0;
+      named_bar_sync(1 + g, kGroupThreads);
+      if (kFull) w_bar += clock64() - tb0;
       prefetch(j + 2);
       const int n = j >> 1, pb = j % kNP;
       wait_acc<kProf>(&sdp_full[g], n & 1, w_full);
       if (prof_me && j == 0) prof[3] = clock64() - t_start;
       wait_acc<kProf>(&pbuf_free[pb], ((j / kNP) & 1) ^ 1, w_pb);      // operand buffer pb no longer read by older MMAs
-      const long long tc0 = kProf ? clock64() : 0;
+      const long long tc0 = kFull ? clock64() : 0;
       tc_fence_after();
       const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
-      const uint32_t taddr = tmem_base + lane_base + g * 128;
-      const uint32_t paddr = tmem_base + lane_base + 256 + pb * 64;
-      // 4 sub-chunks of 16 columns, software pipelined: the TMEM loads of sub-chunk i+1 are in flight while
+      const uint32_t taddr = tmem_base + lane_base + g * 128 + ch * kColsW;
+      const uint32_t paddr = tmem_base + lane_base + 256 + pb * 64 + ch * (kColsW / 2);
+      const float* w_lse = s_lse + ch * kColsW;
+      const float* w_delta = s_delta + ch * kColsW;
+      const int* w_id = s_id + ch * kColsW;
+      // kSub sub-chunks of 16 columns, software pipelined: the TMEM loads of sub-chunk i+1 are in flight while
       // sub-chunk i is computed and its bf16 pairs are stored back to the operand buffer
       uint32_t sv[2][16], dv[2][16];
       tmem_ld16(taddr, sv[0]);
       tmem_ld16(taddr + 64, dv[0]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < kSub; ++i) {
         const int cur = i & 1;
+        const long long tl0 = kFull ? clock64() : 0;
         tmem_wait2_16(sv[cur], dv[cur]);
-        if (i < 3) {
+        if (kFull) { const long long d = clock64() - tl0; if (i == 0) w_ld0 += d; else w_ldn += d; }
+        if (i < kSub - 1) {
           tmem_ld16(taddr + (i + 1) * 16, sv[cur ^ 1]);
           tmem_ld16(taddr + 64 + (i + 1) * 16, dv[cur ^ 1]);
         } else {
-          // every column of this score stage is in registers: hand the stage back to the score-MMA issuer
+          // every column of this warpgroup's part is in registers: hand the stage back to the score-MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sdp_free[g]);
@@ -403,7 +436,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         if (need_mask) {          // tile-level (warp-uniform) branch: only tiles that straddle a label boundary
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const int cid = s_id[i * 16 + e];
+            const int cid = w_id[i * 16 + e];
             const bool hide = (MODE == MODE_DKV) ? (my_id > cid) : (cid > my_id);
             if (hide) sv[cur][e] = 0xff800000u;              // -inf -> P = 0
           }
@@ -412,11 +445,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
           float lse8[8], dl8[8];
-          if (MODE == MODE_DKV) {
-            const float4 l0 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8);
-            const float4 l1 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8 + 4);
-            const float4 d0 = *reinterpret_cast<const float4*>(s_delta + i * 16 + g8 * 8);
-            const float4 d1 = *reinterpret_cast<const float4*>(s_delta + i * 16 + g8 * 8 + 4);
+          if (MODE == MODE_DKV && FK_ATTN_EXP != 3) {
+            const float4 l0 = *reinterpret_cast<const float4*>(w_lse + i * 16 + g8 * 8);
+            const float4 l1 = *reinterpret_cast<const float4*>(w_lse + i * 16 + g8 * 8 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(w_delta + i * 16 + g8 * 8);
+            const float4 d1 = *reinterpret_cast<const float4*>(w_delta + i * 16 + g8 * 8 + 4);
             lse8[0] = l0.x; lse8[1] = l0.y; lse8[2] = l0.z; lse8[3] = l0.w; lse8[4] = l1.x; lse8[5] = l1.y; lse8[6] = l1.z; lse8[7] = l1.w;
             dl8[0] = d0.x; dl8[1] = d0.y; dl8[2] = d0.z; dl8[3] = d0.w; dl8[4] = d1.x; dl8[5] = d1.y; dl8[6] = d1.z; dl8[7] = d1.w;
           } else {
@@ -426,6 +459,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
 #pragma unroll
           for (int e2 = 0; e2 < 4; ++e2) {
             const int i0 = g8 * 8 + e2 * 2;
+#if FK_ATTN_EXP == 4
+            pw[g8 * 4 + e2] = sv[cur][i0] ^ sv[cur][i0 + 1];
+            dw[g8 * 4 + e2] = dv[cur][i0] ^ dv[cur][i0 + 1];
+            continue;
+#endif
             const float p0 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0]), p.scale_log2, -lse8[e2 * 2]));
             const float p1 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0 + 1]), p.scale_log2, -lse8[e2 * 2 + 1]));
             const float s0 = p0 * (__uint_as_float(dv[cur][i0]) - dl8[e2 * 2]);
@@ -435,15 +473,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
           }
         }
         // bf16 pairs -> operand buffer pb (A operand of the accumulate MMAs, TS mode): 8 packed columns each
+#if FK_ATTN_EXP == 2
+        if (pw[0] == 0x12345678u && dw[0] == 0x9abcdef0u) tmem_st8(paddr + i * 8, pw);     // keep the math alive
+#else
         if (MODE == MODE_DKV) tmem_st8(paddr + i * 8, pw);
         tmem_st8(paddr + 32 + i * 8, dw);
+#endif
       }
+      const long long ts0 = kFull ? clock64() : 0;
       tmem_wait_st();
+      if (kFull) w_st += clock64() - ts0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[pb]);
-      if (kProf) w_comp += clock64() - tc0;
+      if (kFull) w_comp += clock64() - tc0;
     }
+    if (prof_me) { prof[15] = w_ld0; prof[16] = w_ldn; prof[17] = w_st; }
     if (prof_me) { prof[4] = w_full; prof[5] = w_pb; prof[6] = w_bar; prof[7] = w_comp; prof[8] = clock64() - t_start; }
     // ---- epilogue: accumulators -> bf16 -> global ----
     mbar_wait(acc_full, 0);
@@ -451,26 +496,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     tc_fence_after();
     const bool writes = (MODE == MODE_DKV) || (g == 1);     // warp-uniform
     if (writes) {
-      const int which = (MODE == MODE_DKV) ? g : 1;      // wg0 -> acc0 (dV), wg1 -> acc1 (dK / dQ)
-      uint32_t acc[32];
+      // parity 0 warpgroups -> acc0 (dV), parity 1 -> acc1 (dK / dQ); column part ch writes its 32 / kNCH columns
+      const int which = (MODE == MODE_DKV) ? g : 1;
+      constexpr int kAcc = 32 / kNCH;
+      static_assert(kAcc == 16 || kAcc == 32, "accumulator split");
+      uint32_t acc[kAcc];
       if (T > 0) {                                        // uniform: the whole warp executes the aligned TMEM load
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + 448 + which * 32, acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;"
-                     : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
-                       "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]), "+r"(acc[14]), "+r"(acc[15]),
-                       "+r"(acc[16]), "+r"(acc[17]), "+r"(acc[18]), "+r"(acc[19]), "+r"(acc[20]), "+r"(acc[21]), "+r"(acc[22]), "+r"(acc[23]),
-                       "+r"(acc[24]), "+r"(acc[25]), "+r"(acc[26]), "+r"(acc[27]), "+r"(acc[28]), "+r"(acc[29]), "+r"(acc[30]), "+r"(acc[31])
-                     :: "memory");
+        const uint32_t aaddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + 448 + which * 32 + ch * kAcc;
+        if constexpr (kAcc == 32) {
+          tmem_ld32(aaddr, *reinterpret_cast<uint32_t(*)[32]>(&acc));
+          tmem_wait1_32(*reinterpret_cast<uint32_t(*)[32]>(&acc));
+        } else {
+          tmem_ld16(aaddr, *reinterpret_cast<uint32_t(*)[16]>(&acc));
+          tmem_wait1_16(*reinterpret_cast<uint32_t(*)[16]>(&acc));
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0u;
+        for (int i = 0; i < kAcc; ++i) acc[i] = 0u;
       }
       if (row_ok) {
         const float sc = (which == 1) ? p.scale : 1.f;
         __nv_bfloat16* dst = (which == 0 ? p.out0 + b * p.o0_bs + static_cast<long long>(row) * p.o0_ts
-                                         : p.out1 + b * p.o1_bs + static_cast<long long>(row) * p.o1_ts) + h * 32;
+                                         : p.out1 + b * p.o1_bs + static_cast<long long>(row) * p.o1_ts) + h * 32 + ch * kAcc;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = 0; c4 < kAcc / 8; ++c4) {
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e)
@@ -488,7 +537,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
-  if (kProf && threadIdx.x == 0) prof[0] = clock64() - t_start;
+  if (kProf && threadIdx.x == 0) {
+    prof[0] = clock64() - t_start;
+    if (kProf == 2) {
+      unsigned long long g_end;
+      unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      prof[20] = static_cast<long long>(g_start); prof[21] = static_cast<long long>(g_end); prof[22] = smid; prof[2] = T;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -878,8 +936,9 @@ FK_API int fk_attn_transpose(const void* x, long long bs, long long ts, int B, i
 }
 
 // Diagnosis only: route fk_attn_backward_tc to the stall-accounting instantiation (prof: int64 [n_ctas, 16]; null = off).
-FK_API int fk_attn_set_profile_buffer(long long* prof) {
+FK_API int fk_attn_set_profile_buffer(long long* prof, int mode) {
   g_attn_prof = prof;
+  g_attn_prof_mode = (mode == 2) ? 2 : 1;
   return FK_OK;
 }
 
@@ -901,10 +960,12 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
   FK_REQUIRE(Sp >= S && Sp % 8 == 0, "fk_attn_backward_tc: Sp must be >= S and a multiple of 8");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess) {
       fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
       return FK_ERR_CUDA;
     }
@@ -941,8 +1002,9 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.out1 = static_cast<__nv_bfloat16*>(dk); p.o1_bs = dk_bs; p.o1_ts = dk_ts;
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = g_attn_prof;
-    if (g_attn_prof) attn_bwd_tc_kernel<MODE_DKV, true><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
-    else attn_bwd_tc_kernel<MODE_DKV, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
+    if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DKV, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
+    else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DKV, 1><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
+    else attn_bwd_tc_kernel<MODE_DKV, 0><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
     FK_CHECK_LAUNCH();
     ++n;
   }
@@ -953,8 +1015,9 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.out0 = nullptr; p.out1 = static_cast<__nv_bfloat16*>(dq); p.o1_bs = dq_bs; p.o1_ts = dq_ts;
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = g_attn_prof;
-    if (g_attn_prof) attn_bwd_tc_kernel<MODE_DQ, true><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
-    else attn_bwd_tc_kernel<MODE_DQ, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
+    if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DQ, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
+    else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DQ, 1><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
+    else attn_bwd_tc_kernel<MODE_DQ, 0><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
     FK_CHECK_LAUNCH();
     ++n;
   }

@@ -139,8 +139,8 @@ int fk_attn_backward(const void* q, const void* k, const void* v, const void* o,
                      const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, int parts, void* stream);
 
 /* Diagnosis only (scripts/gpu_attn_stalls.py): while a buffer is set, fk_attn_backward_tc launches a stall-accounting
- * build of the same kernel that writes int64 [n_ctas, 16] cycle counters (see attention_tc.cu); null switches it off. */
-int fk_attn_set_profile_buffer(long long* prof);
+ * build of the same kernel that writes int64 [n_ctas, 24] cycle counters (see attention_tc.cu); null switches it off. */
+int fk_attn_set_profile_buffer(long long* prof, int mode);   /* mode 1 = full stall accounting, 2 = lifetime + %globaltimer + %smid only */
 
 /* tcgen05 / TMEM / TMA version of the attention backward (attention_tc.cu).  fk_attn_transpose makes the
  * [B][H][32][Sp] copies (zero padded, Sp % 8 == 0) that serve as K-major operands for contractions over tokens:

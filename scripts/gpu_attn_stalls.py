@@ -8,7 +8,8 @@ from frankenstein_b200._lib import lib, ptr, check
 
 NAMES = ["lifetime", "setup", "tiles", "first_scores_ready@", "wg0_wait_sdp_full", "wg0_wait_pbuf_free", "wg0_named_barrier",
          "wg0_compute", "wg0_last_p_ready@", "acc_complete@", "stores_done@", "score_iss_wait_st_full",
-         "score_iss_wait_sdp_free", "acc_iss_wait_p_ready", "producer_wait_st_empty", "-"]
+         "score_iss_wait_sdp_free", "acc_iss_wait_p_ready", "producer_wait_st_empty", "wg0_first_tmem_ld_wait",
+         "wg0_later_tmem_ld_waits", "wg0_tmem_st_wait"]
 
 
 def main():
@@ -20,8 +21,8 @@ def main():
     w = torch.randn(B, S, H * 32, device=dev, dtype=torch.bfloat16)
     n_cta = B * H * (S // 128)
     for parts, name in ((2, "dK/dV kernel"), (4, "dQ kernel")):
-        prof = torch.zeros(n_cta, 16, device=dev, dtype=torch.int64)
-        check(lib().fk_attn_set_profile_buffer(ptr(prof)), "set")
+        prof = torch.zeros(n_cta, 24, device=dev, dtype=torch.int64)
+        check(lib().fk_attn_set_profile_buffer(ptr(prof), 1), "set")
         ops._BWD_PARTS = (parts,)
         for _ in range(2):
             x = qkv.clone().requires_grad_(True)
@@ -29,17 +30,45 @@ def main():
             out.backward(w)
         ops._BWD_PARTS = (2, 4)
         torch.cuda.synchronize()
-        check(lib().fk_attn_set_profile_buffer(None), "unset")
+        check(lib().fk_attn_set_profile_buffer(None, 1), "unset")
         p = prof.double().cpu()
         p = p[p[:, 2] > 0]
         life = p[:, 0].mean().item()
         T = p[:, 2].mean().item()
         print(f"{name}: {p.shape[0]} CTAs, mean tiles {T:.1f}, mean lifetime {life:.0f} cycles = {life / T:.0f} per tile")
-        for i, n in enumerate(NAMES[:15]):
+        for i, n in enumerate(NAMES):
             print(f"  {n:26s} mean {p[:, i].mean().item():9.0f}  ({100 * p[:, i].mean().item() / life:5.1f} % of lifetime)")
         steady = (p[:, 8] - p[:, 3]).mean().item()
         print(f"  steady state (first scores -> last P ready): {steady:.0f} cycles = {steady / T:.0f} per tile; "
               f"prologue {p[:, 3].mean().item():.0f}, tail {(p[:, 0] - p[:, 8]).mean().item():.0f}")
+    # ---- light mode: the product code path plus 2 timestamps per CTA -> true lifetimes and the idle gap between
+    #      consecutive CTAs on one SM (the kernel runs one CTA per SM)
+    for parts, name in ((2, "dK/dV kernel"), (4, "dQ kernel")):
+        prof = torch.zeros(n_cta, 24, device=dev, dtype=torch.int64)
+        check(lib().fk_attn_set_profile_buffer(ptr(prof), 2), "set")
+        ops._BWD_PARTS = (parts,)
+        x = qkv.clone().requires_grad_(True)
+        out = ops.attention_qkv(x * 1.0, H, None, mask)
+        out.backward(w)
+        ops._BWD_PARTS = (2, 4)
+        torch.cuda.synchronize()
+        check(lib().fk_attn_set_profile_buffer(None, 1), "unset")
+        p = prof.cpu()
+        life, T, g0, g1, sm = p[:, 0].double(), p[:, 2].double(), p[:, 20], p[:, 21], p[:, 22]
+        gaps, busy = [], []
+        for s_id in sm.unique().tolist():
+            idx = (sm == s_id).nonzero().flatten()
+            order = idx[g0[idx].argsort()]
+            st, en = g0[order], g1[order]
+            if len(order) > 1:
+                gaps.append((st[1:] - en[:-1]).double())
+            busy.append((en - st).double())
+        gaps = torch.cat(gaps); busy = torch.cat(busy)
+        span = (g1.max() - g0.min()).item()
+        print(f"{name} (light): kernel span {span / 1e3:.1f} us; CTA lifetime mean {life.mean().item():.0f} cycles "
+              f"({busy.mean().item():.0f} ns) = {life.sum().item() / T.sum().item():.0f} cycles per tile; "
+              f"gap between CTAs on an SM: mean {gaps.mean().item():.0f} ns, median {gaps.median().item():.0f} ns; "
+              f"SM busy share {busy.sum().item() / (span * len(sm.unique())):.3f}")
 
 
 if __name__ == "__main__":

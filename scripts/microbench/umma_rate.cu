@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int ts_m
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tb = tslot;
+  const uint32_t tb = __shfl_sync(0xffffffffu, tslot, 0);
   if (style == 2) {
     // two independent issuer threads (warps 0 and 2), half of the MMAs each, different accumulators
     if ((warp == 0 || warp == 2) && lane == 0) {
@@ -49,12 +49,12 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int ts_m
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const int kk = i & 3;
-      const uint32_t d = tb + (i % nacc) * N % 512;
+      const uint32_t d = tb + ((nacc == 2 && (i & 1)) ? 224u : 0u);
       const uint64_t bd = swz64 ? umma_desc_sw64(b + (kk & 1) * 32) : umma_desc_sw128(b + kk * 32);
       const uint64_t ad = swz64 ? umma_desc_sw64(a + (kk & 1) * 32) : umma_desc_sw128(a + kk * 32);
       if (elect_one()) {
-        if (ts_mode) umma_bf16_ts(d, tb + 448 + kk * 8, bd, idesc, i >= nacc);
-        else umma_bf16(d, ad, bd, idesc, i >= nacc);
+        if (ts_mode) umma_bf16_ts(d, tb + 448 + kk * 8, bd, idesc, i >= 2);
+        else umma_bf16(d, ad, bd, idesc, i >= 2);
       }
       __syncwarp();
     }
@@ -90,7 +90,7 @@ int main() {
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   const int iters = 4096;
   printf("style,N,mode,swizzle,nacc,cycles_per_mma,ideal\n");
-  for (int style = 0; style < 3; style += 2)
+  for (int style = 0; style < 3; ++style)
   for (int swz64 = 0; swz64 < 2; ++swz64)
     for (int ts = 0; ts < 2; ++ts)
       for (int N : {32, 64, 128, 256})
