@@ -340,6 +340,12 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const long long o = (row * p.S + slot) * kCand;
           *reinterpret_cast<float4*>(p.cand_val + o) = make_float4(cv[0], cv[1], cv[2], cv[3]);
           *reinterpret_cast<int4*>(p.cand_idx + o) = make_int4(ci[0], ci[1], ci[2], ci[3]);
+          if (t == p.T - 1) {
+            // the CTA that finishes a row block also marks the slots no CTA owns as "no candidate" (row blocks
+            // touched by fewer CTAs than the widest one), so the host never has to clear cand_idx
+            for (int s2 = slot + 2; s2 < p.S; s2 += 2)
+              *reinterpret_cast<int4*>(p.cand_idx + (row * p.S + s2) * kCand) = make_int4(-1, -1, -1, -1);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) m[i] = inf;
@@ -465,13 +471,11 @@ static int search_launch(const void* x_bf16, const void* cb_bf16, const float* c
     }
     attr_set = true;
   }
-  // unused slots must read as "no candidate"
-  if (cudaMemsetAsync(cand_idx, 0xFF, static_cast<size_t>(N) * S * kCand * sizeof(int), stream) != cudaSuccess) return FK_ERR_CUDA;
   if (prof != nullptr)
     vq_search_kernel<true><<<static_cast<unsigned>(G), kSearchThreads, smem_bytes, stream>>>(tx, tcm, p);
   else
     vq_search_kernel<false><<<static_cast<unsigned>(G), kSearchThreads, smem_bytes, stream>>>(tx, tcm, p);
   FK_CHECK_LAUNCH();
-  fk_count_launch(2);
+  fk_count_launch(1);
   return FK_OK;
 }

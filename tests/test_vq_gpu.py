@@ -58,6 +58,27 @@ def test_search_accumulators_match_bf16_gemm(N, K, D):
     assert torch.allclose(v[valid], named[valid], rtol=2e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("N,K,D,ctas", [(1000, 1000, 64, 148), (3000, 700, 64, 37), (5000, 384, 128, 148), (600, 2000, 64, 5),
+                                        (16384, 8192, 256, 148)])
+def test_search_marks_unowned_slots(N, K, D, ctas):
+    """The kernel itself writes 'no candidate' into slots no CTA owns (no host-side clear): poison the buffers first."""
+    fvq, _ = _mods()
+    from frankenstein_b200._lib import lib, ptr, stream, check
+    X, C = random_vq_problem(N, K, D, seed=N + ctas)
+    _, xb, _ = fvq.prepare_input(X.cuda(), False)
+    cb, c2pad = fvq.prepare_codebook(C.cuda(), False)
+    S = lib().fk_vq_search_slots(N, K, ctas)
+    cand_val = torch.full((N, S, fvq.CAND), -1e30, device="cuda")
+    cand_idx = torch.full((N, S, fvq.CAND), 123456789, device="cuda", dtype=torch.int32)
+    check(lib().fk_vq_search(ptr(xb), ptr(cb), ptr(c2pad), N, K, xb.shape[1], 0, ptr(cand_val), ptr(cand_idx), S, ctas,
+                             stream()), "fk_vq_search")
+    torch.cuda.synchronize()
+    assert ((cand_idx == -1) | ((cand_idx >= 0) & (cand_idx < K))).all(), "stale or out-of-range candidate index"
+    score = c2pad[:K][None, :] - 2.0 * (xb.float() @ cb.float().t())
+    flat = cand_idx.view(N, -1)
+    assert (flat == score.argmin(dim=1)[:, None].int()).any(dim=1).all()
+
+
 @pytest.mark.parametrize("cosine", [False, True])
 @pytest.mark.parametrize("N,K,D,kind", [(4096, 512, 64, "clustered"), (4096, 512, 64, "random"),
                                         (16384, 8192, 256, "clustered"), (8192, 8192, 256, "random"),
