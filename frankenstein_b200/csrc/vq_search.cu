@@ -124,11 +124,11 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(c2s + 2 * kBN);
   uint64_t* full = bars;                    // [kMaxStages]
   uint64_t* empty = bars + kMaxStages;      // [kMaxStages]
-  uint64_t* x_full = bars + 2 * kMaxStages;
-  uint64_t* x_empty = x_full + 1;
-  uint64_t* tmem_full = x_full + 2;         // [2 stages][2 halves]
-  uint64_t* tmem_empty = x_full + 6;        // [2 stages][2 halves]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(x_full + 10);
+  uint64_t* x_full = bars + 2 * kMaxStages;  // [4] one per k-slab of X, so the first MMAs start after 32 KB, not 128 KB
+  uint64_t* x_empty = x_full + 4;
+  uint64_t* tmem_full = x_full + 5;         // [2 stages][2 halves]
+  uint64_t* tmem_empty = x_full + 9;        // [2 stages][2 halves]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(x_full + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_start = kProf ? clock64() : 0;
@@ -143,7 +143,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 2);        // both MMA issuers (one per accumulator half) release a slab
     }
-    mbar_init(x_full, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&x_full[i], 1);
     mbar_init(x_empty, 2);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -179,8 +179,10 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
         wait_acc<kProf>(x_empty, (seg & 1) ^ 1, w_xempty);
         if (elect_one()) {
-          mbar_expect_tx(x_full, p.nslab * kXSlabBytes);
-          for (int ks = 0; ks < p.nslab; ++ks) tma_load_2d(Xs + ks * kXSlabBytes, &tmap_x, x_full, ks * kSlabK, rb * kBM);
+          for (int ks = 0; ks < p.nslab; ++ks) {
+            mbar_expect_tx(&x_full[ks], kXSlabBytes);
+            tma_load_2d(Xs + ks * kXSlabBytes, &tmap_x, &x_full[ks], ks * kSlabK, rb * kBM);
+          }
         }
         __syncwarp();
         for (int t = t0; t < t0 + nt; ++t) {
@@ -219,8 +221,6 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (long long u = u_begin; u < u_end; ++seg) {
         const int t0 = static_cast<int>(u % p.T);
         const int nt = static_cast<int>(min(static_cast<long long>(p.T - t0), u_end - u));
-        wait_acc<kProf>(x_full, seg & 1, w_x);
-        tc_fence_after();
         for (int t = 0; t < nt; ++t, ++tc) {
           const uint32_t as = tc & 1;
           wait_acc<kProf>(&tmem_empty[as * 2 + h], ((tc >> 1) & 1) ^ 1, w_te);
@@ -228,6 +228,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const uint32_t d_tmem = tmem_u + (h * 2 + as) * kBN;
           for (int ks = 0; ks < p.nslab; ++ks) {
             const long long c0 = kProf ? clock64() : 0;
+            if (t == 0) wait_acc<kProf>(&x_full[ks], seg & 1, w_x);      // X slab ks of this segment has landed
             wait_acc<kProf>(&full[stage], phase, w_full);
             tc_fence_after();
             const uint64_t adesc = umma_desc_sw128(xs_addr + ks * kXSlabBytes);
