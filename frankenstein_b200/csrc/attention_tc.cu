@@ -595,6 +595,8 @@ attn_transpose_kernel(const __nv_bfloat16* __restrict__ x, long long bs, long lo
 constexpr int kFwdTileK = 128;
 constexpr int kFwdThreads = 384;
 constexpr float kRescaleSlack = 8.f;
+// an optimistic sweep whose scores exceed the stale reference by more than 2^kRedoExcess is redone with the true maximum
+constexpr float kRedoExcess = 60.f;
 
 struct FwdSmem {
   static constexpr int q = 0;                           // 2 x 128 x 64 B
@@ -792,7 +794,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t s_addr = tmem_base + lane_base + g * 128;
     const uint32_t p_addr = tmem_base + lane_base + 256 + g * 64;
     const uint32_t o_addr = tmem_base + lane_base + 384 + g * 32;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_pend = 1.f;
     int pre_i = 0;
     auto prefetch = [&](int j) {
       if (j >= T) return;
@@ -808,72 +810,121 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       prefetch(j + 1);
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
-      // ---- pass 1: row maximum of the (masked) scores; TMEM loads double buffered (next chunk in flight) ----
-      float mx = -INFINITY;
       uint32_t sv[2][32];
-      tmem_ld32(s_addr, sv[0]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cur = c & 1;
-        tmem_wait1_32(sv[cur]);
-        tmem_ld32(s_addr + ((c + 1) & 3) * 32, sv[cur ^ 1]);      // c == 3: chunk 0 again, for pass 2
+      auto mask_chunk = [&](uint32_t (&v)[32], int c) {
         if (need_mask) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (s_id[c * 32 + i] > my_id) sv[cur][i] = 0xff800000u;
+            if (s_id[c * 32 + i] > my_id) v[i] = 0xff800000u;
         }
+      };
+      // O_g *= alpha_pend (rare, warp-uniform): only legal once the previous tile's P V MMAs have retired
+      auto apply_pending = [&]() {
+        if (__any_sync(0xffffffffu, alpha_pend != 1.f)) {
+          uint32_t ov[32];
+          tmem_ld32(o_addr, ov);
+          tmem_wait1_32(ov);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[cur][i]), __uint_as_float(sv[cur][i + 1])));
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha_pend);
+          tmem_st32(o_addr, ov);
+          alpha_pend = 1.f;
+        }
+      };
+      // one sweep over the 128 scores of this row: P = 2^(S c - m_use) -> bf16 pairs into the operand buffer, row sum,
+      // and the raw row maximum on the side; TMEM loads double buffered.  `first_loaded`: chunk 0 is already in flight.
+      float rs = 0.f, mx = -INFINITY;
+      bool released = false, redo = false;
+      auto release_scores = [&]() {                      // S_g fully consumed: the next tile's scores may land
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);
+        released = true;
+      };
+      auto exp_sweep = [&](float m_use, bool optimistic) {
+        rs = 0.f;
+        mx = -INFINITY;
+        if (optimistic) tmem_ld32(s_addr, sv[0]);        // (otherwise chunk 0 was requested by the maximum pass)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cur = c & 1;
+          tmem_wait1_32(sv[cur]);
+          if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, sv[cur ^ 1]);
+          mask_chunk(sv[cur], c);
+          if (optimistic) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[cur][i]), __uint_as_float(sv[cur][i + 1])));
+          }
+          if (c == 3) {
+            // every score is in registers; the optimistic sweep first checks that its stale reference was safe
+            if (optimistic) redo = __any_sync(0xffffffffu, mx * p.scale_log2 > m_run + kRedoExcess);
+            if (!redo) release_scores();
+          }
+          uint32_t pw[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_ex2(fmaf(__uint_as_float(sv[cur][2 * i]), p.scale_log2, -m_use));
+            const float p1 = fast_ex2(fmaf(__uint_as_float(sv[cur][2 * i + 1]), p.scale_log2, -m_use));
+            rs += p0 + p1;
+            pw[i] = pack2(p0, p1);
+          }
+          if (c == 0 && optimistic) {
+            // P_g is reusable and O_g quiescent once the previous tile's P V MMAs have retired
+            mbar_wait(&p_free[g], (j & 1) ^ 1);
+            tc_fence_after();
+            apply_pending();
+          }
+          tmem_st16(p_addr + c * 16, pw);
+        }
+      };
+      const bool two_pass = __any_sync(0xffffffffu, m_run == -INFINITY);
+      if (!two_pass) {
+        // ---- optimistic single sweep against the stale running maximum (softmax is shift invariant; the reference
+        //      only has to keep 2^(s - m) inside the fp32 / bf16 exponent range) ----
+        exp_sweep(m_run, true);
+        const float m_tile = mx * p.scale_log2;
+        if (!redo) {
+          l_run += rs;
+          if (m_tile > m_run + kRescaleSlack) {          // lazy: raise the reference for the tiles to come
+            const float a = fast_ex2(m_run - m_tile);
+            l_run *= a;
+            alpha_pend = a;                              // applied to O_g after this tile's P V MMAs
+            m_run = m_tile;
+          }
+        }
       }
-      // ---- running maximum with lazy rescaling ----
-      const float m_tile = mx * p.scale_log2;
-      const bool raise = m_tile > m_run + kRescaleSlack || m_run == -INFINITY;
-      const float m_new = raise ? fmaxf(m_run, m_tile) : m_run;
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (raise && m_run != -INFINITY) ? fast_ex2(m_run - m_use) : 1.f;
-      // O_g is quiescent once the previous tile's P V MMAs have retired; P_g is then reusable as well
-      mbar_wait(&p_free[g], (j & 1) ^ 1);
-      tc_fence_after();
-      const bool rescale = j > 0 && __any_sync(0xffffffffu, alpha != 1.f);
-      l_run *= alpha;
-      m_run = m_new;
-      // ---- pass 2: P = 2^(S c - m), row sum, bf16 pairs into the operand buffer ----
-      float rs = 0.f;
+      if (two_pass || redo) {
+        // ---- first visible tile of a row (no reference yet) or a jump the stale reference cannot absorb:
+        //      row maximum first, then the sweep ----
+        float mx1 = -INFINITY;
+        tmem_ld32(s_addr, sv[0]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cur = c & 1;                            // chunk 0 was requested by the last step of pass 1
-        tmem_wait1_32(sv[cur]);
-        if (c < 3) {
-          tmem_ld32(s_addr + (c + 1) * 32, sv[cur ^ 1]);
-        } else {                                          // S_g fully consumed: the next tile's scores may land
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[g]);
-        }
-        if (need_mask) {
+        for (int c = 0; c < 4; ++c) {
+          const int cur = c & 1;
+          tmem_wait1_32(sv[cur]);
+          tmem_ld32(s_addr + ((c + 1) & 3) * 32, sv[cur ^ 1]);      // c == 3: chunk 0 again, for the sweep
+          mask_chunk(sv[cur], c);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (s_id[c * 32 + i] > my_id) sv[cur][i] = 0xff800000u;
+          for (int i = 0; i < 32; i += 2) mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[cur][i]), __uint_as_float(sv[cur][i + 1])));
         }
-        uint32_t pw[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_ex2(fmaf(__uint_as_float(sv[cur][2 * i]), p.scale_log2, -m_use));
-          const float p1 = fast_ex2(fmaf(__uint_as_float(sv[cur][2 * i + 1]), p.scale_log2, -m_use));
-          rs += p0 + p1;
-          pw[i] = pack2(p0, p1);
+        const float m_tile = mx1 * p.scale_log2;
+        const bool raise = m_tile > m_run + kRescaleSlack || m_run == -INFINITY;
+        const float m_new = raise ? fmaxf(m_run, m_tile) : m_run;
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = (raise && m_run != -INFINITY) ? fast_ex2(m_run - m_use) : 1.f;
+        if (two_pass) {                                  // (a redone optimistic sweep already waited for p_free)
+          mbar_wait(&p_free[g], (j & 1) ^ 1);
+          tc_fence_after();
+          apply_pending();
         }
-        tmem_st16(p_addr + c * 16, pw);
+        l_run *= alpha;
+        alpha_pend = alpha;
+        apply_pending();                                 // O_g *= alpha before this tile accumulates
+        m_run = m_new;
+        redo = false;
+        exp_sweep(m_use, false);
+        l_run += rs;
       }
-      if (rescale) {                                      // rare: O_g *= alpha (warp-uniform branch)
-        uint32_t ov[32];
-        tmem_ld32(o_addr, ov);
-        tmem_wait1_32(ov);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-        tmem_st32(o_addr, ov);
-      }
-      l_run += rs;
+      if (!released) release_scores();
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -893,7 +944,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int i = 0; i < 32; ++i) ov[i] = 0u;
     }
     if (row_ok) {
-      const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+      const float inv = (l_run > 0.f) ? alpha_pend / l_run : 0.f;      // a reference raise after the last tile is still owed to O
       __nv_bfloat16* dst = p.out + b * p.o_bs + static_cast<long long>(row) * p.o_ts + h * 32;
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {

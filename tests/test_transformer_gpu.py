@@ -65,6 +65,27 @@ def test_attention_fwd_bwd(kind, B, S, H, impl, monkeypatch):
     close(x.grad, ref_in.grad, rtol=3e-2, what=f"attention dqkv {kind}")
 
 
+@pytest.mark.parametrize("growth", [0.02, 0.2, 2.0])
+def test_attention_forward_running_max_paths(growth):
+    """Scores that keep growing along the key axis: per 128-key tile the row maximum rises by less than the lazy-rescale
+    slack (growth 0.02), by more than the slack (0.2: deferred O rescale) and by more than the optimistic sweep can absorb
+    (2.0: the tile is redone with its true maximum) -- forward values must match fp32 SDPA in every regime."""
+    from frankenstein_b200 import ops
+    B, S, H = 1, 1024, 2
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(7)
+    u = torch.nn.functional.normalize(torch.randn(32, generator=g), dim=0)
+    q = torch.randn(B, S, H, 32, generator=g) * 0.3 + u * math.sqrt(32.0) * math.log(2.0)     # q.u*scale ~ ln 2 per unit of k.u
+    k = torch.randn(B, S, H, 32, generator=g) * 0.3 + u * (growth * torch.arange(S).float())[None, :, None, None]
+    v = torch.randn(B, S, H, 32, generator=g)
+    qkv = torch.stack([q, k, v], dim=2).reshape(B, S, 3 * H * 32).to(dev).to(torch.bfloat16)
+    out = ops.attention_qkv(qkv.clone(), H, None, None)
+    qf, kf, vf = qkv.float().view(B, S, 3, H, 32).unbind(2)
+    ref = F.scaled_dot_product_attention(qf.transpose(1, 2), kf.transpose(1, 2), vf.transpose(1, 2)).transpose(1, 2)
+    assert torch.isfinite(out.float()).all()
+    close(out.reshape(B, S, H, 32), ref, what=f"running-max path, growth {growth}")
+
+
 @pytest.mark.parametrize("per_sample", [False, True])
 def test_rope_matches_reference_formula(per_sample):
     from frankenstein_b200 import ops
