@@ -183,8 +183,11 @@ class CausalCrossAttention(nn.Module):
         B, T, _ = x.shape
         S = context.shape[1]
         q = _linear_bf16(x, self.qw.weight).view(B, T, self.n_heads, -1).transpose(1, 2)
-        kv = _linear_bf16(context, torch.cat([self.kw.weight, self.vw.weight], dim=0)).view(B, S, 2, self.n_heads, -1)
-        k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
+        # two projections instead of one fused [k|v] GEMM: slicing a fused buffer costs a zero-fill + strided copy per
+        # slice in autograd (select_backward), more than the second GEMM launch
+        ctx_bf16 = context.to(BF16)
+        k = F.linear(ctx_bf16, self.kw.weight.to(BF16)).view(B, S, self.n_heads, -1).transpose(1, 2)
+        v = F.linear(ctx_bf16, self.vw.weight.to(BF16)).view(B, S, self.n_heads, -1).transpose(1, 2)
         res = _dense_mask_attention(q, k, v, attn_mask)
         res = res.transpose(1, 2).reshape(B, T, -1)
         return _linear_bf16(res, self.project.weight)
@@ -228,19 +231,27 @@ class Block(nn.Module):
         return x
 
 
-def run_blocks(blocks, h, attn_mask=None, rope=None, final_norm=None, final_dtype=torch.float32):
+def run_blocks(blocks, h, attn_mask=None, rope=None, final_norm=None, final_dtype=torch.float32, h_delta=None):
     """A stack of pre-LN Blocks on the fp32 residual stream `h` with every `x = x + branch` fused into the LayerNorm
     that follows it (ops.add_layer_norm): identical math to calling the Blocks one after another
     (models/brainformer.py:242-245, 345-351), one pass over the residual stream per add+norm instead of three.
-    Returns (h, y) where y = final_norm(h) if final_norm is given, else None."""
+    Returns (h, y) where y = final_norm(h) if final_norm is given, else None.
+    h_delta (bf16): the stream starts as h + h_delta with h [1, S, D] broadcast over the batch (embedding table +
+    patch projection, brainformer.py:343); the sum is formed inside the first fused add+LayerNorm."""
     n = len(blocks)
+    if h_delta is not None and not (n > 0 and h.dtype == torch.float32 and isinstance(blocks[0].ln_1, _KernelLayerNorm)):
+        h, h_delta = h_delta.float() + h, None
     if n == 0:
         return h, (final_norm(h, out_dtype=final_dtype) if final_norm is not None else None)
     if h.dtype != torch.float32 or not isinstance(blocks[0].ln_1, _KernelLayerNorm):
         for blk in blocks:                                   # generic path (e.g. RMSNorm blocks, bf16 streams)
             h = blk(h, attn_mask=attn_mask, rope=rope)
         return h, (final_norm(h, out_dtype=final_dtype) if final_norm is not None else None)
-    y = blocks[0].ln_1(h)
+    if h_delta is not None:
+        l0 = blocks[0].ln_1
+        h, y = ops.add_layer_norm(h, h_delta, l0.weight, l0.bias, l0.eps)
+    else:
+        y = blocks[0].ln_1(h)
     for i, blk in enumerate(blocks):
         a = blk.attn(y, attn_mask, rope)
         h, y = ops.add_layer_norm(h, a, blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
@@ -334,10 +345,11 @@ class Encoder(nn.Module):
     def embed(self, patches):
         return _linear_bf16(patches, self.transformer.emb.weight, self.transformer.emb.bias)
 
-    def forward(self, x, kv_cache=None):
+    def forward(self, x, kv_cache=None, out_dtype=torch.float32):
+        """out_dtype: dtype of the final LayerNorm output (the perceiver asks for bf16, the operand type of its GEMMs)."""
         patches = self.to_patches(x)
         b, n_tokens, _ = patches.shape
-        h = self.embed(patches) + self.spatial_pos_embedding[:, -n_tokens:]          # fp32 residual stream
+        emb = self.spatial_pos_embedding[:, -n_tokens:].float()       # [1, S, dim]; added inside the first add+LayerNorm
         mask = LabelMask.block_causal(b, n_tokens, self.n_electrodes, x.device)
         if n_tokens != self.block_size:
             # the reference slices attn_mask[-T:, -T:] and rope[-T:]: labels of the LAST n_tokens positions
@@ -345,7 +357,7 @@ class Encoder(nn.Module):
             ids = ((torch.arange(n_tokens, device=x.device) + first) // self.n_electrodes).to(torch.int32)
             mask = LabelMask(ids[None].expand(b, n_tokens).contiguous())
         rope = RopeSpec(self.rope_table(), None, self.block_size - n_tokens)
-        _, y = run_blocks(self.transformer.h, h, mask, rope, self.transformer.ln_f)
+        _, y = run_blocks(self.transformer.h, emb, mask, rope, self.transformer.ln_f, out_dtype, h_delta=self.embed(patches))
         return y
 
 
@@ -463,7 +475,7 @@ class BrainFormer(nn.Module):
 
     def forward(self, x, targets=None, date_info=None):
         b = x.shape[0]
-        context = self.encoder(x)
+        context = self.encoder(x, out_dtype=BF16)
         h = self.learnable_queries.expand(b, self.n_output_tokens, -1)
         for cross_block in self.perceiver.h:
             h = cross_block(h, context, self.self_attn_mask, self.cross_attn_mask, sa_rope=self.rope_cache)

@@ -41,13 +41,15 @@ template <typename TIn, typename TOut, int MAXV>
 __global__ void __launch_bounds__(kNormWarps * 32)
 norm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, TOut* __restrict__ y,
                 float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int D, float eps, int rms,
-                const __nv_bfloat16* __restrict__ delta = nullptr, float* __restrict__ x_out = nullptr) {
+                const __nv_bfloat16* __restrict__ delta = nullptr, float* __restrict__ x_out = nullptr, long long x_period = 0) {
   // delta / x_out (fp32 residual stream only): x_new = x + delta is written to x_out and normalised, fusing the
-  // residual add of the transformer block into the norm that follows it
+  // residual add of the transformer block into the norm that follows it.  x_period > 0: x has only x_period rows
+  // and is broadcast over the batch (row % x_period) -- the positional / electrode embedding added to the patch
+  // embedding (models/brainformer.py:343) without materialising the sum first.
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kNormWarps + (threadIdx.x >> 5);
   if (row >= M) return;
-  const TIn* xr = x + row * D;
+  const TIn* xr = x + (x_period > 0 ? row % x_period : row) * D;
   float v[MAXV][4];
   float s = 0.f;
 #pragma unroll
@@ -248,14 +250,15 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ h13, const __nv_bfloat16* __
 
 template <typename TIn, typename TOut>
 static int launch_norm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, long long M, int D,
-                           float eps, int rms, cudaStream_t stream, const __nv_bfloat16* delta = nullptr, float* x_out = nullptr) {
+                           float eps, int rms, cudaStream_t stream, const __nv_bfloat16* delta = nullptr, float* x_out = nullptr,
+                           long long x_period = 0) {
   const unsigned grid = static_cast<unsigned>((M + kNormWarps - 1) / kNormWarps);
   const TIn* xi = static_cast<const TIn*>(x);
   TOut* yo = static_cast<TOut*>(y);
-  if (D <= 128) norm_fwd_kernel<TIn, TOut, 1><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out);
-  else if (D <= 256) norm_fwd_kernel<TIn, TOut, 2><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out);
-  else if (D <= 512) norm_fwd_kernel<TIn, TOut, 4><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out);
-  else if (D <= 1024) norm_fwd_kernel<TIn, TOut, 8><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out);
+  if (D <= 128) norm_fwd_kernel<TIn, TOut, 1><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out, x_period);
+  else if (D <= 256) norm_fwd_kernel<TIn, TOut, 2><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out, x_period);
+  else if (D <= 512) norm_fwd_kernel<TIn, TOut, 4><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out, x_period);
+  else if (D <= 1024) norm_fwd_kernel<TIn, TOut, 8><<<grid, kNormWarps * 32, 0, stream>>>(xi, w, b, yo, mean, rstd, M, D, eps, rms, delta, x_out, x_period);
   else return FK_ERR_UNSUPPORTED;
   return FK_OK;
 }
@@ -340,16 +343,18 @@ FK_API int fk_swiglu_backward(const void* h13, const void* gy, void* dh13, long 
 
 // Fused residual add + norm (fp32 residual stream): x_new = x + delta (bf16), y = norm(x_new).  Replaces the pair
 // `x = x + branch(...)` ; `ln(x)` of models/brainformer.py:243-244 (one pass over the residual stream instead of two).
+// x_period > 0: x holds x_period rows and is broadcast over the batch (embedding + patch projection, brainformer.py:343).
 FK_API int fk_add_norm_forward(const float* x, const void* delta_bf16, const float* weight, const float* bias, float* x_out,
                                void* y, int y_dtype, float* mean, float* rstd, long long M, int D, float eps, int rms,
-                               void* stream_) {
+                               long long x_period, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(x && delta_bf16 && weight && x_out && y && rstd && M > 0 && D > 0 && D % 4 == 0, "fk_add_norm_forward: bad argument");
   FK_REQUIRE(rms || mean, "fk_add_norm_forward: LayerNorm needs the mean buffer");
+  FK_REQUIRE(x_period >= 0 && (x_period == 0 || M % x_period == 0), "fk_add_norm_forward: M must be a multiple of x_period");
   const __nv_bfloat16* dl = static_cast<const __nv_bfloat16*>(delta_bf16);
   int rc = FK_ERR_UNSUPPORTED;
-  if (y_dtype == 1) rc = launch_norm_fwd<float, __nv_bfloat16>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream, dl, x_out);
-  else if (y_dtype == 0) rc = launch_norm_fwd<float, float>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream, dl, x_out);
+  if (y_dtype == 1) rc = launch_norm_fwd<float, __nv_bfloat16>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream, dl, x_out, x_period);
+  else if (y_dtype == 0) rc = launch_norm_fwd<float, float>(x, weight, bias, y, mean, rstd, M, D, eps, rms, stream, dl, x_out, x_period);
   if (rc != FK_OK) { fk_set_last_error("fk_add_norm_forward: unsupported dtype or D > 1024", __FILE__, __LINE__); return rc; }
   FK_CHECK_LAUNCH();
   fk_count_launch();

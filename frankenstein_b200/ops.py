@@ -83,15 +83,22 @@ class _AddNormFn(torch.autograd.Function):
             raise FkError("add_norm expects an fp32 residual stream and a bf16 branch output")
         D = x.shape[-1]
         xc, dc = x.contiguous(), delta.contiguous()
-        M = xc.numel() // D
+        M = dc.numel() // D
+        period = 0
+        if xc.numel() != dc.numel():
+            # x [1, S, D] broadcast over the batch of delta [B, S, D] (embedding table + patch projection)
+            if xc.dim() != dc.dim() or xc.shape[0] != 1 or xc.shape[1:] != dc.shape[1:]:
+                raise FkError("add_norm: x must match delta or be [1, ...] broadcast over its leading dimension")
+            period = xc.numel() // D
+        ctx.x_bcast = period > 0
         w = weight.detach().float().contiguous()
         b = bias.detach().float().contiguous() if bias is not None else None
-        x_new = torch.empty_like(xc)
-        y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+        x_new = torch.empty(dc.shape, device=x.device, dtype=torch.float32)
+        y = torch.empty(dc.shape, device=x.device, dtype=out_dtype)
         mean = None if rms else torch.empty(M, device=x.device, dtype=torch.float32)
         rstd = torch.empty(M, device=x.device, dtype=torch.float32)
         check(lib().fk_add_norm_forward(ptr(xc), ptr(dc), ptr(w), ptr(b), ptr(x_new), ptr(y), _DT[out_dtype], ptr(mean),
-                                        ptr(rstd), M, D, float(eps), int(rms), stream()), "fk_add_norm_forward")
+                                        ptr(rstd), M, D, float(eps), int(rms), period, stream()), "fk_add_norm_forward")
         ctx.save_for_backward(x_new, w, mean if mean is not None else torch.empty(0, device=x.device), rstd)
         ctx.rms, ctx.has_bias, ctx.w_dtype = rms, bias is not None, weight.dtype
         return x_new, y
@@ -118,6 +125,8 @@ class _AddNormFn(torch.autograd.Function):
                                          M, D, int(ctx.rms), stream()), "fk_add_norm_backward")
         dw = dwp.sum(0).to(ctx.w_dtype)
         db = dbp.sum(0).to(ctx.w_dtype) if ctx.has_bias else None
+        if ctx.x_bcast:
+            dx = dx.sum(0, keepdim=True)
         return dx, dx16, dw, db, None, None, None
 
 

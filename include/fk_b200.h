@@ -167,7 +167,9 @@ int fk_attn_forward_tc(const void* q, const void* k, const void* vt, int Sp, voi
  * (g_res nullable = gradient reaching x_out through the residual path), written as fp32 and, if dx_bf16 != NULL, as a
  * bf16 copy for the delta branch.  y / g_y dtype codes as fk_norm_forward. */
 int fk_add_norm_forward(const float* x, const void* delta_bf16, const float* weight, const float* bias, float* x_out,
-                        void* y, int y_dtype, float* mean, float* rstd, long long M, int D, float eps, int rms, void* stream);
+                        void* y, int y_dtype, float* mean, float* rstd, long long M, int D, float eps, int rms,
+                        long long x_period /* > 0: x has x_period rows, broadcast over the batch (brainformer.py:343) */,
+                        void* stream);
 int fk_add_norm_backward(const float* x_new, const void* g_y, int g_dtype, const float* g_res, const float* weight,
                          const float* mean, const float* rstd, float* dx, void* dx_bf16, float* dw_part, float* db_part,
                          long long M, int D, int rms, void* stream);
