@@ -37,9 +37,9 @@ CPU_SAMPLE_TRIALS = 2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 # (attention rows: the capture in profiles/r01_attention_tc_ncu_full.txt is a 16-trial launch; trials are independent,
 #  so a B-trial launch moves B/16 times those bytes)
-NCU_TRAFFIC = {"vq_search": 12659712}
-NCU_TRAFFIC_PER_16_TRIALS = {"attn_fwd": 201787904 + 55185408, "attn_bwd_dkv": 411350528 + 119061248,
-                             "attn_bwd_dq": 344237568 + 60145664}
+NCU_TRAFFIC = {"vq_search": 12660224}
+NCU_TRAFFIC_PER_16_TRIALS = {"attn_fwd": 201665792 + 54162944, "attn_bwd_dkv": 411375872 + 119109888,
+                             "attn_bwd_dq": 344237568 + 61068800}
 
 
 def model_configs():
@@ -160,7 +160,7 @@ def cpu_reference_run(steps, warmup, trials=CPU_SAMPLE_TRIALS):
         loss.backward()
         torch.nn.utils.clip_grad_value_(params, 1.0)
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()
@@ -280,7 +280,7 @@ def main():
     launches = _lib.launch_count()
     ksum = _lib.TIMER.summary()
     clk = clocks.stop()
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # ---- timed region 2: end to end (pinned host batch -> device every step, loss read back every step) ----
     xd = torch.empty_like(pool[0][0])
