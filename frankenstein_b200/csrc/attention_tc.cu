@@ -82,7 +82,8 @@ struct TcSmem {
 };
 
 // FK_ATTN_EXP (diagnosis builds only, results are WRONG): 1 = no MUFU, 2 = no TMEM operand stores, 3 = no stats LDS,
-// 4 = no math at all between the TMEM loads and stores.
+// 4 = no math at all between the TMEM loads and stores, 5 = no delta subtraction (and no delta LDS),
+// 6 = neither delta nor lse (P = ex2(S * c)).
 #ifndef FK_ATTN_EXP
 #define FK_ATTN_EXP 0
 #endif
@@ -464,10 +465,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
             dw[g8 * 4 + e2] = dv[cur][i0] ^ dv[cur][i0 + 1];
             continue;
 #endif
+#if FK_ATTN_EXP == 6
+            const float p0 = fast_ex2(__uint_as_float(sv[cur][i0]) * p.scale_log2);
+            const float p1 = fast_ex2(__uint_as_float(sv[cur][i0 + 1]) * p.scale_log2);
+#else
             const float p0 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0]), p.scale_log2, -lse8[e2 * 2]));
             const float p1 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0 + 1]), p.scale_log2, -lse8[e2 * 2 + 1]));
+#endif
+#if FK_ATTN_EXP == 5 || FK_ATTN_EXP == 6
+            const float s0 = p0 * __uint_as_float(dv[cur][i0]);           // what folding delta into the dP MMA would leave
+            const float s1 = p1 * __uint_as_float(dv[cur][i0 + 1]);
+#else
             const float s0 = p0 * (__uint_as_float(dv[cur][i0]) - dl8[e2 * 2]);
             const float s1 = p1 * (__uint_as_float(dv[cur][i0 + 1]) - dl8[e2 * 2 + 1]);
+#endif
             if (MODE == MODE_DKV) pw[g8 * 4 + e2] = pack2(p0, p1);
             dw[g8 * 4 + e2] = pack2(s0, s1);
           }

@@ -126,12 +126,34 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// try_wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint elapses,
+// instead of re-issuing the probe every ~40 cycles and taking issue slots from the compute warps of its scheduler.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+  return ok != 0;
+}
+#ifndef FK_MBAR_HINT_NS
+#define FK_MBAR_HINT_NS 1000
+#endif
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if FK_MBAR_HINT_NS > 0
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, FK_MBAR_HINT_NS)) {
+    if (clock64() - t0 > (1ll << 33)) __trap();
+  }
+#else
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
   }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
