@@ -82,7 +82,8 @@ def test_search_marks_unowned_slots(N, K, D, ctas):
 @pytest.mark.parametrize("cosine", [False, True])
 @pytest.mark.parametrize("N,K,D,kind", [(4096, 512, 64, "clustered"), (4096, 512, 64, "random"),
                                         (16384, 8192, 256, "clustered"), (8192, 8192, 256, "random"),
-                                        (1000, 333, 64, "random"), (5, 7, 64, "random")])
+                                        (1000, 333, 64, "random"), (5, 7, 64, "random"),
+                                        (4096, 16384, 256, "random"), (2048, 65536, 256, "clustered")])   # cfg-5 sweep ends
 def test_eval_forward_matches_oracle(N, K, D, kind, cosine):
     fvq, ovq = _mods()
     if kind == "clustered":
@@ -143,6 +144,33 @@ def test_train_step_matches_oracle(B, T, K, D, cosine):
         for name in ("cluster_size", "embed_avg", "embed"):
             a, b = getattr(mine._codebook, name).cpu(), getattr(ref._codebook, name)
             assert torch.allclose(a, b, rtol=RTOL, atol=1e-5), (step, name, (a - b).abs().max())
+
+
+@pytest.mark.parametrize("cosine", [False, True])
+def test_ema_trajectory_ten_steps(cosine):
+    """Codebook state after 1 and after 10 EMA steps (SURVEY 8c fixture list): clustered inputs with a clear margin, so no
+    near-tie can flip an assignment and the two trajectories must stay together to fp32 round-off."""
+    fvq, ovq = _mods()
+    B, T, K, D = 4, 128, 128, 64
+    X, C = make_vq_problem(B * T, K, D, seed=11, cosine=cosine, noise=0.1)
+    ref = ovq.VectorQuantizeRef(dim=D, codebook_size=K, commitment_weight=0.25, use_cosine_sim=cosine,
+                                threshold_ema_dead_code=0).train()
+    ref._codebook.embed.copy_(C[None]); ref._codebook.embed_avg.copy_(C[None]); ref._codebook.cluster_size.fill_(1.0)
+    mine = fvq.VectorQuantize(dim=D, codebook_size=K, commitment_weight=0.25, use_cosine_sim=cosine,
+                              threshold_ema_dead_code=0).cuda().train()
+    mine.load_state_dict(ref.state_dict())
+    mine._kmeans_initted_host = True
+    g = torch.Generator().manual_seed(13)
+    for step in range(10):
+        x = (X + 0.02 * torch.randn(X.shape, generator=g)).view(B, T, D)
+        _, i_ref, l_ref = ref(x)
+        _, i, l = mine(x.cuda())
+        assert torch.equal(i.cpu(), i_ref), f"assignment differs at step {step}"
+        if step in (0, 9):
+            assert torch.allclose(l.cpu(), l_ref, rtol=1e-4, atol=1e-7)
+            for name in ("cluster_size", "embed_avg", "embed"):
+                a, b = getattr(mine._codebook, name).cpu(), getattr(ref._codebook, name)
+                assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), (step, name, (a - b).abs().max())
 
 
 @pytest.mark.parametrize("cosine", [False, True])
