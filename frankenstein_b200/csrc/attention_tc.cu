@@ -48,6 +48,9 @@ struct TcParams {
   int B, H, S_row, S_col, Sq;
   float scale, scale_log2;
   long long* prof;                                     // kProf instantiation: [n_ctas][16] cycle counters
+  int mn_major;                                        // 1: the accumulate MMAs read their B operand (Q / dO / K tile,
+                                                       // [64 tokens][32 dims]) MN-major from the score stage itself;
+                                                       // 0: K-major from transposed copies (tm_tA / tm_tB)
 };
 
 // Diagnosis only (scripts/gpu_attn_stalls.py): when a buffer is set, fk_attn_backward_tc launches the stall-accounting
@@ -272,11 +275,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         uint8_t* st = smem + TcSmem::stream + stage * 16384;
         wait_acc<kProf>(&st_empty[stage], phase ^ 1, w_se);
         if (elect_one()) {
-          mbar_expect_tx(&st_full[stage], kStageBytes);
+          mbar_expect_tx(&st_full[stage], p.mn_major ? 8192u : kStageBytes);
           tma_load_4d(st, &tm_stA, &st_full[stage], 0, h, t * kCols, b);
           tma_load_4d(st + 4096, &tm_stB, &st_full[stage], 0, h, t * kCols, b);
-          if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[stage], t * kCols, (b * p.H + h) * 32);
-          tma_load_2d(st + 12288, &tm_tB, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+          if (!p.mn_major) {
+            if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+            tma_load_2d(st + 12288, &tm_tB, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+          }
         }
         __syncwarp();
         if (++stage == kNST) { stage = 0; phase ^= 1; }
@@ -327,16 +332,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         const int stage = ia % kNST, pb = ia % kNP;
         wait_acc<kProf>(&p_ready[pb], (ia / kNP) & 1, w_pr);
         tc_fence_after();
-        const uint64_t dTA = umma_desc_sw128(stream + stage * 16384 + 8192), dTB = umma_desc_sw128(stream + stage * 16384 + 12288);
         const uint32_t ta = tmem_u + 256 + pb * 64;       // P at +0..31, dS at +32..63 (bf16 pairs)
-        if (elect_one()) {
+        if (p.mn_major) {
+          // B operand straight from the score stage: tile [64 tokens][32 dims], 64-byte rows, SWIZZLE_64B = the canonical
+          // MN-major layout (N = 32 dims contiguous, 8-token groups 512 B apart); a K step of 16 tokens = 1024 B.
+          // DKV: dV += P^T dO (stB), dK += dS^T Q (stA).  DQ: dQ += dS K (stA).
+          const uint64_t dMA = umma_desc_sw64(stream + stage * 16384 + 4096), dMB = umma_desc_sw64(stream + stage * 16384);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + 448, ta + kk * 8, dTA + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
-            umma_bf16_ts(tmem_u + 480, ta + 32 + kk * 8, dTB + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + 448, ta + kk * 8, dMA + 64 * kk, idesc_acc | (1u << 16), (ia > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_ts(tmem_u + 480, ta + 32 + kk * 8, dMB + 64 * kk, idesc_acc | (1u << 16), (ia > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&pbuf_free[pb]);
+            umma_commit(&st_empty[stage]);
           }
-          umma_commit(&pbuf_free[pb]);
-          umma_commit(&st_empty[stage]);
+        } else {
+          const uint64_t dTA = umma_desc_sw128(stream + stage * 16384 + 8192), dTB = umma_desc_sw128(stream + stage * 16384 + 12288);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + 448, ta + kk * 8, dTA + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_ts(tmem_u + 480, ta + 32 + kk * 8, dTB + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&pbuf_free[pb]);
+            umma_commit(&st_empty[stage]);
+          }
         }
         __syncwarp();
       }
@@ -1044,15 +1065,20 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
   rc |= make_tmap_heads_sw64(&mK64, k, B, S, H, k_bs, k_ts, kCols);
   rc |= make_tmap_heads_sw64(&mV64, v, B, S, H, v_bs, v_ts, kCols);
   const uint64_t trows = static_cast<uint64_t>(B) * H * 32;
-  if (parts & 2) {
+  // qt / kt / dot all null: the accumulate MMAs take their B operand MN-major from the [tokens][32] tiles (no copies)
+  const int mn_major = (qt == nullptr && kt == nullptr && dot == nullptr) ? 1 : 0;
+  mQt = mQ64; mDOt = mDO64; mKt = mK64;
+  if ((parts & 2) && !mn_major) {
     FK_REQUIRE(qt && dot && dk && dv, "fk_attn_backward_tc: dK/dV needs qt, dot, dk, dv");
     rc |= make_tmap_bf16_sw128(&mQt, qt, trows, static_cast<uint64_t>(Sp), 32);
     rc |= make_tmap_bf16_sw128(&mDOt, dot, trows, static_cast<uint64_t>(Sp), 32);
   }
-  if (parts & 4) {
+  if ((parts & 4) && !mn_major) {
     FK_REQUIRE(kt && dq, "fk_attn_backward_tc: dQ needs kt, dq");
     rc |= make_tmap_bf16_sw128(&mKt, kt, trows, static_cast<uint64_t>(Sp), 32);
   }
+  FK_REQUIRE(!(parts & 2) || (dk && dv), "fk_attn_backward_tc: dK/dV needs dk, dv");
+  FK_REQUIRE(!(parts & 4) || dq, "fk_attn_backward_tc: dQ needs dq");
   if (rc != 0) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
   const dim3 grid((S + kRows - 1) / kRows, H, B);
   int n = 0;
@@ -1064,6 +1090,7 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.out1 = static_cast<__nv_bfloat16*>(dk); p.o1_bs = dk_bs; p.o1_ts = dk_ts;
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = g_attn_prof;
+    p.mn_major = mn_major;
     if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DKV, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
     else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DKV, 1><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
     else attn_bwd_tc_kernel<MODE_DKV, 0><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
@@ -1077,6 +1104,7 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.out0 = nullptr; p.out1 = static_cast<__nv_bfloat16*>(dq); p.o1_bs = dq_bs; p.o1_ts = dq_ts;
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = g_attn_prof;
+    p.mn_major = mn_major;
     if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DQ, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
     else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DQ, 1><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
     else attn_bwd_tc_kernel<MODE_DQ, 0><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);

@@ -19,6 +19,9 @@ import os
 # attention backward implementation: "tc" = tcgen05/TMEM/TMA kernels (attention_tc.cu), "legacy" = mma.sync kernels
 ATTN_BWD_IMPL = os.environ.get("FK_ATTN_BWD", "tc")
 ATTN_FWD_IMPL = os.environ.get("FK_ATTN_FWD", "tc")
+# B operand of the backward accumulate MMAs: "mn" = MN-major straight from the [tokens][32] tiles (no copies),
+# "transposed" = K-major from token-contiguous copies made by fk_attn_transpose (cross-check path)
+ATTN_BWD_OPERANDS = os.environ.get("FK_ATTN_BWD_OPERANDS", "mn")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -326,16 +329,19 @@ class _AttnQKVFn(torch.autograd.Function):
             legacy("attn_bwd_dkv", 2)
             legacy("attn_bwd_dq", 4)
         else:
-            # tcgen05 path: K-major (token-contiguous) copies of q, k, dO for the contractions over tokens
+            # tcgen05 path
             Sp = (S + 7) // 8 * 8
             d4 = d_o.view(B, S, H, hd)
-            tr = {}
-            with timed("attn_transpose"):
-                for name, src in (("q", q), ("k", k), ("do", d4)):
-                    t = torch.empty(B, H, hd, Sp, device=qkv.device, dtype=torch.bfloat16)
-                    check(lib().fk_attn_transpose(ptr(src), src.stride(0), src.stride(1), B, S, H, hd, ptr(t), Sp, stream()),
-                          "fk_attn_transpose")
-                    tr[name] = t
+            tr = {"q": None, "k": None, "do": None}
+            if ATTN_BWD_OPERANDS == "transposed":
+                # K-major (token-contiguous) copies of q, k, dO for the contractions over tokens; the default reads the
+                # [tokens][32] tiles MN-major instead and needs no copies
+                with timed("attn_transpose"):
+                    for name, src in (("q", q), ("k", k), ("do", d4)):
+                        t = torch.empty(B, H, hd, Sp, device=qkv.device, dtype=torch.bfloat16)
+                        check(lib().fk_attn_transpose(ptr(src), src.stride(0), src.stride(1), B, S, H, hd, ptr(t), Sp, stream()),
+                              "fk_attn_transpose")
+                        tr[name] = t
             for name, part in (("attn_bwd_dkv", 2), ("attn_bwd_dq", 4)):
                 if part not in _BWD_PARTS:
                     continue
