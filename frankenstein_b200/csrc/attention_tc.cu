@@ -651,7 +651,7 @@ struct FwdParams {
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                   const __grid_constant__ CUtensorMap tm_vt, const FwdParams p) {
+                   const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
@@ -684,7 +684,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   }
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_vt); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < kNST; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 2); }
@@ -752,8 +752,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (elect_one()) {
           mbar_expect_tx(&st_full[stage], 16384);
           tma_load_4d(st, &tm_k, &st_full[stage], 0, h, t * kFwdTileK, b);
-          tma_load_2d(st + 8192, &tm_vt, &st_full[stage], t * kFwdTileK, (b * p.H + h) * 32);
-          tma_load_2d(st + 12288, &tm_vt, &st_full[stage], t * kFwdTileK + 64, (b * p.H + h) * 32);
+          tma_load_4d(st + 8192, &tm_v, &st_full[stage], 0, h, t * kFwdTileK, b);      // V tile [128 keys][32 dims]
         }
         __syncwarp();
         if (++stage == kNST) { stage = 0; phase ^= 1; }
@@ -795,7 +794,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t stream = smem_u32(smem + FwdSmem::stream);
       for (int j = 0; j < T_u; ++j) {
         const int stage = j % kNST;
-        const uint64_t dV0 = umma_desc_sw128(stream + stage * 16384 + 8192), dV1 = umma_desc_sw128(stream + stage * 16384 + 12288);
+        // V tile [128 keys][32 dims] (64-byte rows, SWIZZLE_64B) read MN-major: N = dims contiguous, K = keys, a K step of
+        // 16 keys = 1024 B -- no transposed copy of V exists
+        const uint64_t dV = umma_desc_sw64(stream + stage * 16384 + 8192);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           mbar_wait(&p_ready[g], j & 1);
@@ -804,7 +805,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
-              umma_bf16_ts(oa, pa + kk * 8, (kk < 4 ? dV0 : dV1) + 2 * (kk & 3), idesc, (j > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_ts(oa, pa + kk * 8, dV + 64 * kk, idesc | (1u << 16), (j > 0 || kk > 0) ? 1u : 0u);
             umma_commit(&p_free[g]);
             umma_commit(&st_empty[stage]);
           }
@@ -1115,18 +1116,17 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
   return FK_OK;
 }
 
-// Forward on tcgen05.  vt = fk_attn_transpose(v) ([B][H][32][Sp]); same label / range conventions as fk_attn_forward.
-FK_API int fk_attn_forward_tc(const void* q, const void* k, const void* vt, int Sp, void* out, float* lse, int B, int H, int S,
-                              int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long o_bs,
-                              long long o_ts, const int* qid, const int* kid, const int* qmin, const int* qmax, const int* kmin,
-                              const int* kmax, float scale, void* stream_) {
+// Forward on tcgen05; q / k / v are strided views of the fused projection; same label / range conventions as fk_attn_forward.
+FK_API int fk_attn_forward_tc(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S,
+                              int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
+                              long long v_ts, long long o_bs, long long o_ts, const int* qid, const int* kid, const int* qmin,
+                              const int* qmax, const int* kmin, const int* kmax, float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(head_dim == 32, "fk_attn_forward_tc: only head_dim 32 is built");
-  FK_REQUIRE(q && k && vt && out && B > 0 && H > 0 && S > 0, "fk_attn_forward_tc: bad argument");
+  FK_REQUIRE(q && k && v && out && B > 0 && H > 0 && S > 0, "fk_attn_forward_tc: bad argument");
   FK_REQUIRE((qid == nullptr) == (kid == nullptr), "fk_attn_forward_tc: qid and kid go together");
   FK_REQUIRE(qid == nullptr || (qmin && qmax && kmin && kmax), "fk_attn_forward_tc: label ranges missing");
   FK_REQUIRE((S + kFwdTileK - 1) / kFwdTileK <= kMaxTiles && S < (1 << 20), "fk_attn_forward_tc: sequence too long");
-  FK_REQUIRE(Sp >= S && Sp % 8 == 0, "fk_attn_forward_tc: Sp must be >= S and a multiple of 8");
   FK_REQUIRE(o_ts % 8 == 0 && o_bs % 8 == 0, "fk_attn_forward_tc: output strides must keep 16-byte alignment");
   static bool attr_set = false;
   if (!attr_set) {
@@ -1136,17 +1136,17 @@ FK_API int fk_attn_forward_tc(const void* q, const void* k, const void* vt, int 
     }
     attr_set = true;
   }
-  CUtensorMap mQ, mK, mVt;
+  CUtensorMap mQ, mK, mV;
   int rc = 0;
   rc |= make_tmap_heads_sw64(&mQ, q, B, S, H, q_bs, q_ts, 128);
   rc |= make_tmap_heads_sw64(&mK, k, B, S, H, k_bs, k_ts, kFwdTileK);
-  rc |= make_tmap_bf16_sw128(&mVt, vt, static_cast<uint64_t>(B) * H * 32, static_cast<uint64_t>(Sp), 32);
+  rc |= make_tmap_heads_sw64(&mV, v, B, S, H, v_bs, v_ts, kFwdTileK);
   if (rc != 0) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
   FwdParams p = {};
   p.qid = qid; p.kid = kid; p.qmin = qmin; p.qmax = qmax; p.kmin = kmin; p.kmax = kmax;
   p.out = static_cast<__nv_bfloat16*>(out); p.lse = lse; p.o_bs = o_bs; p.o_ts = o_ts;
   p.B = B; p.H = H; p.Sq = S; p.Sk = S; p.scale_log2 = scale * 1.4426950408889634f;
-  attn_fwd_tc_kernel<<<dim3((S + 255) / 256, H, B), kFwdThreads, FwdSmem::total, stream>>>(mQ, mK, mVt, p);
+  attn_fwd_tc_kernel<<<dim3((S + 255) / 256, H, B), kFwdThreads, FwdSmem::total, stream>>>(mQ, mK, mV, p);
   FK_CHECK_LAUNCH();
   fk_count_launch();
   return FK_OK;

@@ -286,15 +286,10 @@ class _AttnQKVFn(torch.autograd.Function):
                                             q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                                             out.stride(0), out.stride(1), *margs, stream()), "fk_attn_forward")
         else:
-            Sp = (S + 7) // 8 * 8
-            vt = torch.empty(B, H, hd, Sp, device=qkv.device, dtype=torch.bfloat16)
-            with timed("attn_transpose"):
-                check(lib().fk_attn_transpose(ptr(v), v.stride(0), v.stride(1), B, S, H, hd, ptr(vt), Sp, stream()),
-                      "fk_attn_transpose")
             with timed("attn_fwd"):
-                check(lib().fk_attn_forward_tc(ptr(q), ptr(k), ptr(vt), Sp, ptr(out), ptr(lse), B, H, S, hd,
-                                               q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
-                                               *margs, stream()), "fk_attn_forward_tc")
+                check(lib().fk_attn_forward_tc(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, hd,
+                                               q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                               out.stride(0), out.stride(1), *margs, stream()), "fk_attn_forward_tc")
         ctx.save_for_backward(qkv, out, lse)
         ctx.rope, ctx.mask, ctx.scale, ctx.H = rope, mask, scale, H
         return out

@@ -142,8 +142,9 @@ int fk_attn_backward(const void* q, const void* k, const void* v, const void* o,
  * build of the same kernel that writes int64 [n_ctas, 24] cycle counters (see attention_tc.cu); null switches it off. */
 int fk_attn_set_profile_buffer(long long* prof, int mode);   /* mode 1 = full stall accounting, 2 = lifetime + %globaltimer + %smid only */
 
-/* tcgen05 / TMEM / TMA version of the attention backward (attention_tc.cu).  fk_attn_transpose makes the
- * [B][H][32][Sp] copies (zero padded, Sp % 8 == 0) that serve as K-major operands for contractions over tokens:
+/* tcgen05 / TMEM / TMA version of the attention backward (attention_tc.cu).  qt = kt = dot = NULL (default): the
+ * contractions over tokens read the Q / dO / K tiles MN-major straight from the strided inputs.  Cross-check mode:
+ * fk_attn_transpose makes [B][H][32][Sp] copies (zero padded, Sp % 8 == 0) that serve as K-major operands instead:
  * qt, dot for dK/dV (parts & 2), kt for dQ (parts & 4).  delta must already hold rowsum(dO*O)
  * (fk_attn_backward with parts = 1).  Same labels / ranges / strides conventions as fk_attn_backward; Sq == Sk == S. */
 int fk_attn_transpose(const void* x, long long bs, long long ts, int B, int S, int H, int head_dim, void* xt, int Sp,
@@ -156,11 +157,12 @@ int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void*
                         long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
                         const int* kmin, const int* kmax, float scale, int parts, void* stream);
 
-/* tcgen05 / TMEM / TMA forward (attention_tc.cu): vt = fk_attn_transpose(v) ([B][H][32][Sp]); Sq == Sk == S. */
-int fk_attn_forward_tc(const void* q, const void* k, const void* vt, int Sp, void* out, float* lse, int B, int H, int S,
-                       int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long o_bs,
-                       long long o_ts, const int* qid, const int* kid, const int* qmin, const int* qmax, const int* kmin,
-                       const int* kmax, float scale, void* stream);
+/* tcgen05 / TMEM / TMA forward (attention_tc.cu): q / k / v are strided views ([B][S][H][32], strides in elements);
+ * the V tile is read MN-major by the P V MMAs, so no transposed copy is needed; Sq == Sk == S. */
+int fk_attn_forward_tc(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S,
+                       int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
+                       long long v_ts, long long o_bs, long long o_ts, const int* qid, const int* kid, const int* qmin,
+                       const int* qmax, const int* kmin, const int* kmax, float scale, void* stream);
 
 /* Fused residual add + norm on the fp32 residual stream: x_out = x + delta (bf16), y = norm(x_out)
  * (the pair `x = x + branch(...)`; `ln(x)` of models/brainformer.py:243-244).  Backward: dx = norm_backward(g_y) + g_res
