@@ -5,21 +5,21 @@
 // score tiles live in TMEM, and each compute thread owns one resident row, so the per-row statistics never
 // need a shuffle.  Two launches of one kernel template:
 //
-//   MODE_DKV  CTA owns 128 keys (resident K, V), streams 64-query tiles (Q, dO + their transposes Qt, dOt):
+//   MODE_DKV  CTA owns 128 keys (resident K, V), streams 64-query tiles (Q, dO):
 //             S^T = K Q^T, dP^T = V dO^T  (TMEM)  ->  P^T = 2^(S^T c - lse[q]),  dS^T = P^T (dP^T - delta[q])
-//             -> bf16 operands in smem  ->  dV += P^T dO,  dK += dS^T Q  (TMEM accumulators, 32 columns each)
-//   MODE_DQ   CTA owns 128 queries (resident Q, dO), streams 64-key tiles (K, V + Kt):
+//             -> bf16 operands in TMEM  ->  dV += P^T dO,  dK += dS^T Q  (TMEM accumulators, 32 columns each)
+//   MODE_DQ   CTA owns 128 queries (resident Q, dO), streams 64-key tiles (K, V):
 //             S = Q K^T, dP = dO V^T  ->  P, dS  ->  dQ += dS K
 //
-// Pipeline per CTA (384 threads): warp 0 = TMA producer (4-stage ring of streamed tiles), warp 1 = MMA issuer
+// Pipeline per CTA (512 threads): warp 0 = TMA producer (8-stage ring of streamed tiles), warp 1 = MMA issuer
 // of the score products, warp 2 = TMEM allocator, warp 3 = builds the list of visible tiles, then issues the
-// accumulate MMAs, warps 4-7 / 8-11 = two compute warpgroups that alternate tiles, each with
-// tiles round-robin over three TMEM score stages.  P / dS never touch shared memory: a compute thread packs its
-// row to bf16 and writes it back into the stage's own TMEM columns (tcgen05.st), and the accumulate MMAs read
-// that as their A operand straight from TMEM (TS mode) -- the smem data pipe, which bounds an SS-mode version of
-// this kernel, only carries the streamed operands.  Operand layouts: [tokens][32] tiles are TMA-loaded with the
-// 64-byte swizzle (K-major, K = head dim); the transposed [32][tokens] tiles use the 128-byte swizzle (K-major,
-// K = tokens).
+// accumulate MMAs, warps 4-15 = three compute warpgroups, one per TMEM score stage (tile j belongs to warpgroup
+// j % 3), so three tiles are in flight.  P / dS never touch shared memory: a compute thread packs its row to bf16 and
+// writes it back IN PLACE over the fp32 score columns it has already consumed (tcgen05.st), and the accumulate MMAs
+// read that as their A operand straight from TMEM (TS mode); their B operand is the streamed [tokens][32] tile itself,
+// read MN-major (K = tokens), the same tile that served the score MMA as a K-major operand (K = head dim).  Tiles are
+// TMA-loaded with the 64-byte swizzle.  The smem data pipe, which bounds an SS-mode version of this kernel, only
+// carries the streamed operands.
 #include "common.cuh"
 #include "tma_host.cuh"
 
@@ -28,14 +28,13 @@ namespace fk {
 constexpr int kRows = 128;        // resident rows per CTA (UMMA M)
 constexpr int kCols = 64;         // streamed tile (UMMA N of the score MMAs, K of the accumulate MMAs)
 constexpr int kNST = 8;           // streamed smem stages
-constexpr int kNP = 3;            // TMEM operand buffers for P | dS (bf16 pairs, 64 columns each)
-// TMEM map (512 columns): score stage of warpgroup g at g*128 (S 64 | dP 64); operand buffer b at 256 + b*64
-// (P 32 | dS 32); accumulators at 448 (dV) and 480 (dK / dQ).
-constexpr int kNCH = 2;           // column halves of a score tile, one compute warpgroup each (per tile parity)
-constexpr int kColsW = kCols / kNCH;          // score columns per warpgroup
-constexpr int kSub = kColsW / 16;             // 16-column sub-chunks per warpgroup and tile
-constexpr int kGroupThreads = 128 * kNCH;     // compute threads that share a tile
-constexpr int kTcThreads = 128 + 2 * kGroupThreads;
+constexpr int kNG = 3;            // score stages in TMEM = tiles in flight = compute warpgroups (tile j belongs to j % kNG)
+// TMEM map (512 columns): score stage g at g*128 (S 64 | dP 64 fp32 columns).  The compute warpgroup overwrites its
+// stage IN PLACE with the bf16 operands of the accumulate MMAs (P pairs at +0..31, dS pairs at +64..95), so no separate
+// operand buffers exist and three tiles fit; accumulators at 384 (dV) and 416 (dK / dQ).
+constexpr int kSub = kCols / 16;              // 16-column sub-chunks per tile
+constexpr int kTcThreads = 128 + 128 * kNG;
+constexpr int kAccCol = 128 * kNG;
 constexpr int kMaxTiles = 2048;   // streamed tiles per sequence (S <= 131072); entries carry a flag in bit 15
 constexpr int MODE_DKV = 0, MODE_DQ = 1;
 
@@ -55,8 +54,8 @@ struct TcParams {
 
 // Diagnosis only (scripts/gpu_attn_stalls.py): when a buffer is set, fk_attn_backward_tc launches the stall-accounting
 // instantiation, which writes per CTA: 0 lifetime, 1 setup, 2 tiles, 3 first score stage ready, 4 sum wait sdp_full,
-// 5 sum wait pbuf_free, 6 sum named barrier, 7 sum compute, 8 last p_ready, 9 accumulators complete, 10 stores done,
-// 11 score issuer wait st_full, 12 score issuer wait sdp_free, 13 acc issuer wait p_ready, 14 producer wait st_empty
+// 5 (unused), 6 sum named barrier, 7 sum compute, 8 last p_ready, 9 accumulators complete, 10 stores done,
+// 11 score issuer wait st_full, 12 score issuer wait stage_free, 13 acc issuer wait p_ready, 14 producer wait st_empty
 // (3..10 by warpgroup 0, warp 4, lane 0; times since CTA start).
 static long long* g_attn_prof = nullptr;
 static int g_attn_prof_mode = 1;   // 1 = full stall accounting, 2 = light (lifetime + global timestamps + SM id)
@@ -79,7 +78,7 @@ struct TcSmem {
   static constexpr int resB = 8192;
   static constexpr int stream = 16384;                 // kNST x 16 KB: stA | stB | tA | tB (4 KB each)
   static constexpr int stats = stream + kNST * 16384;  // [2 wg][2 buffers][lse | delta | id][64] x 4 B           // [2 wg][lse | delta | id][64] x 4 B
-  static constexpr int tiles = stats + 2 * 2 * 3 * 64 * 4; // uint16 visible-tile list
+  static constexpr int tiles = stats + kNG * 2 * 3 * 64 * 4; // uint16 visible-tile list
   static constexpr int bars = tiles + kMaxTiles * 2;
   static constexpr int total = bars + 256;
 };
@@ -167,11 +166,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   uint64_t* res_full = bars;               // [1]
   uint64_t* st_full = bars + 1;            // [kNST]
   uint64_t* st_empty = bars + 1 + kNST;    // [kNST]
-  uint64_t* sdp_full = bars + 1 + 2 * kNST;   // [2]    score stage of warpgroup g written by the tensor core
-  uint64_t* sdp_free = sdp_full + 2;       // [2]    ... read out into registers (4 warps arrive)
-  uint64_t* p_ready = sdp_free + 2;        // [kNP]  P / dS operand buffer written (4 warps arrive)
-  uint64_t* pbuf_free = p_ready + kNP;     // [kNP]  accumulate MMAs that read the buffer have retired
-  uint64_t* acc_full = pbuf_free + kNP;    // [1]
+  uint64_t* sdp_full = bars + 1 + 2 * kNST;   // [kNG]  score stage g written by the tensor core
+  uint64_t* stage_free = sdp_full + kNG;   // [kNG]  the accumulate MMAs that read stage g (as P / dS) have retired
+  uint64_t* p_ready = stage_free + kNG;    // [kNG]  P / dS written in place into stage g (4 warps arrive)
+  uint64_t* acc_full = p_ready + kNG;      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   int* n_tiles_slot = reinterpret_cast<int*>(acc_full + 1) + 1;
   uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + TcSmem::tiles);
@@ -204,13 +202,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   if (warp == 1 && lane == 0) {
     mbar_init(res_full, 1);
     for (int i = 0; i < kNST; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kNG; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&sdp_free[i], 4 * kNCH);
-    }
-    for (int i = 0; i < kNP; ++i) {
-      mbar_init(&p_ready[i], 4 * kNCH);
-      mbar_init(&pbuf_free[i], 1);
+      mbar_init(&stage_free[i], 1);
+      mbar_init(&p_ready[i], 4);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -303,9 +298,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       tc_fence_after();
       long long w_sf = 0, w_free = 0;
       for (int js = 0; js < T_u; ++js) {
-        const int stage = js % kNST, g = js & 1;
+        const int stage = js % kNST, g = js % kNG, n = js / kNG;
         wait_acc<kProf>(&st_full[stage], (js / kNST) & 1, w_sf);
-        wait_acc<kProf>(&sdp_free[g], ((js >> 1) & 1) ^ 1, w_free);
+        wait_acc<kProf>(&stage_free[g], (n & 1) ^ 1, w_free);
         tc_fence_after();
         const uint64_t dS = umma_desc_sw64(stream + stage * 16384), dD = umma_desc_sw64(stream + stage * 16384 + 4096);
         if (elect_one()) {
@@ -329,10 +324,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       const uint32_t stream = smem_u32(smem + TcSmem::stream);
       long long w_pr = 0;
       for (int ia = 0; ia < T_u; ++ia) {
-        const int stage = ia % kNST, pb = ia % kNP;
-        wait_acc<kProf>(&p_ready[pb], (ia / kNP) & 1, w_pr);
+        const int stage = ia % kNST, g = ia % kNG, n = ia / kNG;
+        wait_acc<kProf>(&p_ready[g], n & 1, w_pr);
         tc_fence_after();
-        const uint32_t ta = tmem_u + 256 + pb * 64;       // P at +0..31, dS at +32..63 (bf16 pairs)
+        const uint32_t ta = tmem_u + g * 128;             // P pairs at +0..31, dS pairs at +64..95 (written in place)
         if (p.mn_major) {
           // B operand straight from the score stage: tile [64 tokens][32 dims], 64-byte rows, SWIZZLE_64B = the canonical
           // MN-major layout (N = 32 dims contiguous, 8-token groups 512 B apart); a K step of 16 tokens = 1024 B.
@@ -341,10 +336,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + 448, ta + kk * 8, dMA + 64 * kk, idesc_acc | (1u << 16), (ia > 0 || kk > 0) ? 1u : 0u);
-              umma_bf16_ts(tmem_u + 480, ta + 32 + kk * 8, dMB + 64 * kk, idesc_acc | (1u << 16), (ia > 0 || kk > 0) ? 1u : 0u);
+              if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + kAccCol, ta + kk * 8, dMA + 64 * kk, idesc_acc | (1u << 16), (ia > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_ts(tmem_u + kAccCol + 32, ta + 64 + kk * 8, dMB + 64 * kk, idesc_acc | (1u << 16), (ia > 0 || kk > 0) ? 1u : 0u);
             }
-            umma_commit(&pbuf_free[pb]);
+            umma_commit(&stage_free[g]);
             umma_commit(&st_empty[stage]);
           }
         } else {
@@ -352,10 +347,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + 448, ta + kk * 8, dTA + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
-              umma_bf16_ts(tmem_u + 480, ta + 32 + kk * 8, dTB + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+              if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + kAccCol, ta + kk * 8, dTA + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_ts(tmem_u + kAccCol + 32, ta + 64 + kk * 8, dTB + 2 * kk, idesc_acc, (ia > 0 || kk > 0) ? 1u : 0u);
             }
-            umma_commit(&pbuf_free[pb]);
+            umma_commit(&stage_free[g]);
             umma_commit(&st_empty[stage]);
           }
         }
@@ -367,14 +362,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     }
   } else if (warp >= 4) {
     // ================================ compute warpgroups ================================
-    // 2 * kNCH warpgroups: tile parity g x column part ch.  The warpgroups of one parity share a score stage (each
-    // reads its own kColsW columns) so four warps per scheduler keep the MUFU / FMA pipes fed while others wait on TMEM.
-    const int wgi = (warp - 4) >> 2;
-    const int g = wgi & 1;                       // tile parity
-    const int ch = wgi >> 1;                     // column part of the tile
+    // kNG warpgroups, one per score stage: warpgroup g owns the tiles j with j % kNG == g, reads S / dP of its stage and
+    // writes P / dS back in place.
+    const int g = (warp - 4) >> 2;               // warpgroup = score stage
     const int q4 = warp & 3;                     // TMEM lane quarter
     const int r = q4 * 32 + lane;                // resident row owned by this thread
-    const int tid = ch * 128 + r;                // index within the parity group
+    const int tid = r;                           // index within the warpgroup
     const int row = r0 + r;
     const bool row_ok = row < p.S_row;
     float* stats_base = reinterpret_cast<float*>(smem + TcSmem::stats) + g * 384;
@@ -390,7 +383,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     float pre_f = 0.f;
     int pre_i = 0;
     auto prefetch = [&](int j) {
-      if (j >= T || tid >= 128) return;
+      if (j >= T) return;
       const int c = (tile_list[j] & 0x7fff) * kCols + (tid & 63);
       const bool ok = c < p.S_col;
       if (MODE == MODE_DKV) {
@@ -405,60 +398,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       }
     };
     prefetch(g);
-    long long w_full = 0, w_pb = 0, w_bar = 0, w_comp = 0, w_ld0 = 0, w_ldn = 0, w_st = 0;
+    long long w_full = 0, w_bar = 0, w_comp = 0;
     const bool prof_me = kFull && warp == 4 && lane == 0;
-    for (int j = g; j < T; j += 2) {
+    for (int j = g; j < T; j += kNG) {
+      const int n = j / kNG;
       const bool need_mask = (tile_list[j] & 0x8000) != 0;
-      // column statistics: double buffered per parity group, so one barrier per tile (write -> barrier -> read; the
+      // column statistics: double buffered per warpgroup, so one barrier per tile (write -> barrier -> read; the
       // previous tile's readers use the other buffer)
-      float* s_lse = stats_base + ((j >> 1) & 1) * 192;
+      float* s_lse = stats_base + (n & 1) * 192;
       float* s_delta = s_lse + 64;
       int* s_id = reinterpret_cast<int*>(s_lse + 128);
       if (MODE == MODE_DKV) {
-        if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else if (tid < 128) { s_delta[tid - 64] = pre_f; }
+        if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else { s_delta[tid - 64] = pre_f; }
       } else if (tid < 64) {
         s_id[tid] = pre_i;
       }
       const long long tb0 = kFull ? clock64() : 0;
-      named_bar_sync(1 + g, kGroupThreads);
+      named_bar_sync(1 + g, 128);
       if (kFull) w_bar += clock64() - tb0;
-      prefetch(j + 2);
-      const int n = j >> 1, pb = j % kNP;
+      prefetch(j + kNG);
       wait_acc<kProf>(&sdp_full[g], n & 1, w_full);
       if (prof_me && j == 0) prof[3] = clock64() - t_start;
-      wait_acc<kProf>(&pbuf_free[pb], ((j / kNP) & 1) ^ 1, w_pb);      // operand buffer pb no longer read by older MMAs
       const long long tc0 = kFull ? clock64() : 0;
       tc_fence_after();
-      const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
-      const uint32_t taddr = tmem_base + lane_base + g * 128 + ch * kColsW;
-      const uint32_t paddr = tmem_base + lane_base + 256 + pb * 64 + ch * (kColsW / 2);
-      const float* w_lse = s_lse + ch * kColsW;
-      const float* w_delta = s_delta + ch * kColsW;
-      const int* w_id = s_id + ch * kColsW;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + g * 128;
       // kSub sub-chunks of 16 columns, software pipelined: the TMEM loads of sub-chunk i+1 are in flight while
-      // sub-chunk i is computed and its bf16 pairs are stored back to the operand buffer
+      // sub-chunk i is computed and its bf16 pairs are stored over columns this thread has already consumed
+      // (sub-chunk i occupies fp32 columns 16 i .. 16 i + 15, its pairs go to 8 i .. 8 i + 7)
       uint32_t sv[2][16], dv[2][16];
       tmem_ld16(taddr, sv[0]);
       tmem_ld16(taddr + 64, dv[0]);
 #pragma unroll
       for (int i = 0; i < kSub; ++i) {
         const int cur = i & 1;
-        const long long tl0 = kFull ? clock64() : 0;
         tmem_wait2_16(sv[cur], dv[cur]);
-        if (kFull) { const long long d = clock64() - tl0; if (i == 0) w_ld0 += d; else w_ldn += d; }
         if (i < kSub - 1) {
           tmem_ld16(taddr + (i + 1) * 16, sv[cur ^ 1]);
           tmem_ld16(taddr + 64 + (i + 1) * 16, dv[cur ^ 1]);
-        } else {
-          // every column of this warpgroup's part is in registers: hand the stage back to the score-MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sdp_free[g]);
         }
         if (need_mask) {          // tile-level (warp-uniform) branch: only tiles that straddle a label boundary
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const int cid = w_id[i * 16 + e];
+            const int cid = s_id[i * 16 + e];
             const bool hide = (MODE == MODE_DKV) ? (my_id > cid) : (cid > my_id);
             if (hide) sv[cur][e] = 0xff800000u;              // -inf -> P = 0
           }
@@ -468,10 +449,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         for (int g8 = 0; g8 < 2; ++g8) {
           float lse8[8], dl8[8];
           if (MODE == MODE_DKV && FK_ATTN_EXP != 3) {
-            const float4 l0 = *reinterpret_cast<const float4*>(w_lse + i * 16 + g8 * 8);
-            const float4 l1 = *reinterpret_cast<const float4*>(w_lse + i * 16 + g8 * 8 + 4);
-            const float4 d0 = *reinterpret_cast<const float4*>(w_delta + i * 16 + g8 * 8);
-            const float4 d1 = *reinterpret_cast<const float4*>(w_delta + i * 16 + g8 * 8 + 4);
+            const float4 l0 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8);
+            const float4 l1 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(s_delta + i * 16 + g8 * 8);
+            const float4 d1 = *reinterpret_cast<const float4*>(s_delta + i * 16 + g8 * 8 + 4);
             lse8[0] = l0.x; lse8[1] = l0.y; lse8[2] = l0.z; lse8[3] = l0.w; lse8[4] = l1.x; lse8[5] = l1.y; lse8[6] = l1.z; lse8[7] = l1.w;
             dl8[0] = d0.x; dl8[1] = d0.y; dl8[2] = d0.z; dl8[3] = d0.w; dl8[4] = d1.x; dl8[5] = d1.y; dl8[6] = d1.z; dl8[7] = d1.w;
           } else {
@@ -504,54 +485,42 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
             dw[g8 * 4 + e2] = pack2(s0, s1);
           }
         }
-        // bf16 pairs -> operand buffer pb (A operand of the accumulate MMAs, TS mode): 8 packed columns each
+        // bf16 pairs back into the stage (A operand of the accumulate MMAs, TS mode): 8 packed columns each
 #if FK_ATTN_EXP == 2
-        if (pw[0] == 0x12345678u && dw[0] == 0x9abcdef0u) tmem_st8(paddr + i * 8, pw);     // keep the math alive
+        if (pw[0] == 0x12345678u && dw[0] == 0x9abcdef0u) tmem_st8(taddr + i * 8, pw);     // keep the math alive
 #else
-        if (MODE == MODE_DKV) tmem_st8(paddr + i * 8, pw);
-        tmem_st8(paddr + 32 + i * 8, dw);
+        if (MODE == MODE_DKV) tmem_st8(taddr + i * 8, pw);
+        tmem_st8(taddr + 64 + i * 8, dw);
 #endif
       }
-      const long long ts0 = kFull ? clock64() : 0;
       tmem_wait_st();
-      if (kFull) w_st += clock64() - ts0;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[pb]);
+      if (lane == 0) mbar_arrive(&p_ready[g]);
       if (kFull) w_comp += clock64() - tc0;
     }
-    if (prof_me) { prof[15] = w_ld0; prof[16] = w_ldn; prof[17] = w_st; }
-    if (prof_me) { prof[4] = w_full; prof[5] = w_pb; prof[6] = w_bar; prof[7] = w_comp; prof[8] = clock64() - t_start; }
+    if (prof_me) { prof[4] = w_full; prof[6] = w_bar; prof[7] = w_comp; prof[8] = clock64() - t_start; }
     // ---- epilogue: accumulators -> bf16 -> global ----
     mbar_wait(acc_full, 0);
     if (prof_me) prof[9] = clock64() - t_start;
     tc_fence_after();
-    const bool writes = (MODE == MODE_DKV) || (g == 1);     // warp-uniform
+    const bool writes = (MODE == MODE_DKV) ? (g < 2) : (g == 1);     // warp-uniform: wg0 -> acc0 (dV), wg1 -> acc1 (dK / dQ)
     if (writes) {
-      // parity 0 warpgroups -> acc0 (dV), parity 1 -> acc1 (dK / dQ); column part ch writes its 32 / kNCH columns
       const int which = (MODE == MODE_DKV) ? g : 1;
-      constexpr int kAcc = 32 / kNCH;
-      static_assert(kAcc == 16 || kAcc == 32, "accumulator split");
-      uint32_t acc[kAcc];
+      uint32_t acc[32];
       if (T > 0) {                                        // uniform: the whole warp executes the aligned TMEM load
-        const uint32_t aaddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + 448 + which * 32 + ch * kAcc;
-        if constexpr (kAcc == 32) {
-          tmem_ld32(aaddr, *reinterpret_cast<uint32_t(*)[32]>(&acc));
-          tmem_wait1_32(*reinterpret_cast<uint32_t(*)[32]>(&acc));
-        } else {
-          tmem_ld16(aaddr, *reinterpret_cast<uint32_t(*)[16]>(&acc));
-          tmem_wait1_16(*reinterpret_cast<uint32_t(*)[16]>(&acc));
-        }
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + kAccCol + which * 32, acc);
+        tmem_wait1_32(acc);
       } else {
 #pragma unroll
-        for (int i = 0; i < kAcc; ++i) acc[i] = 0u;
+        for (int i = 0; i < 32; ++i) acc[i] = 0u;
       }
       if (row_ok) {
         const float sc = (which == 1) ? p.scale : 1.f;
         __nv_bfloat16* dst = (which == 0 ? p.out0 + b * p.o0_bs + static_cast<long long>(row) * p.o0_ts
-                                         : p.out1 + b * p.o1_bs + static_cast<long long>(row) * p.o1_ts) + h * 32 + ch * kAcc;
+                                         : p.out1 + b * p.o1_bs + static_cast<long long>(row) * p.o1_ts) + h * 32;
 #pragma unroll
-        for (int c4 = 0; c4 < kAcc / 8; ++c4) {
+        for (int c4 = 0; c4 < 4; ++c4) {
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e)

@@ -6,9 +6,9 @@ import torch
 from frankenstein_b200 import ops
 from frankenstein_b200._lib import lib, ptr, check
 
-NAMES = ["lifetime", "setup", "tiles", "first_scores_ready@", "wg0_wait_sdp_full", "wg0_wait_pbuf_free", "wg0_named_barrier",
+NAMES = ["lifetime", "setup", "tiles", "first_scores_ready@", "wg0_wait_sdp_full", "(unused)", "wg0_named_barrier",
          "wg0_compute", "wg0_last_p_ready@", "acc_complete@", "stores_done@", "score_iss_wait_st_full",
-         "score_iss_wait_sdp_free", "acc_iss_wait_p_ready", "producer_wait_st_empty", "wg0_first_tmem_ld_wait",
+         "score_iss_wait_stage_free", "acc_iss_wait_p_ready", "producer_wait_st_empty", "wg0_first_tmem_ld_wait",
          "wg0_later_tmem_ld_waits", "wg0_tmem_st_wait"]
 
 
