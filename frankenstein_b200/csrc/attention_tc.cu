@@ -79,7 +79,7 @@ struct TcSmem {
   static constexpr int stream = 16384;                 // kNST x 16 KB: stA | stB | tA | tB (4 KB each)
   static constexpr int stats = stream + kNST * 16384;  // [2 wg][2 buffers][lse | delta | id][64] x 4 B           // [2 wg][lse | delta | id][64] x 4 B
   static constexpr int tiles = stats + kNG * 2 * 3 * 64 * 4; // uint16 visible-tile list
-  static constexpr int bars = tiles + kMaxTiles * 2;
+  static constexpr int bars = tiles + 2 * kMaxTiles * 2;   // two lists: the next item's is built while this one runs
   static constexpr int total = bars + 256;
 };
 
@@ -155,6 +155,11 @@ __device__ __forceinline__ void tmem_wait1_32(uint32_t (&a)[32]) {
                :: "memory");
 }
 
+// Work-item hand-out of the persistent backward kernels: [mode][0] = next item, [mode][1] = CTAs that have finished;
+// the last CTA to finish puts both back to zero, so no host-side reset (and no extra launch) is needed.  One launch per
+// mode at a time (the library is driven from one stream per process, like the rest of the ABI).
+__device__ unsigned int g_bwd_items[2][2];
+
 template <int MODE, int kProf>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_constant__ CUtensorMap tm_resB,
@@ -171,28 +176,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   uint64_t* p_ready = stage_free + kNG;    // [kNG]  P / dS written in place into stage g (4 warps arrive)
   uint64_t* acc_full = p_ready + kNG;      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  int* n_tiles_slot = reinterpret_cast<int*>(acc_full + 1) + 1;
-  uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + TcSmem::tiles);
+  int* n_tiles_slot = reinterpret_cast<int*>(acc_full + 1) + 1;   // [2]
+  int* item_slot = reinterpret_cast<int*>(acc_full + 1) + 3;      // [2]: item ids handed to this CTA, double buffered
+  uint16_t* tile_lists = reinterpret_cast<uint16_t*>(smem + TcSmem::tiles);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int r0 = rt * kRows;
   constexpr bool kFull = kProf == 1;
-  const long long t_start = kProf ? clock64() : 0;
-  unsigned long long g_start = 0;
-  if (kProf == 2 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
-  long long* prof = kProf ? p.prof + ((static_cast<long long>(b) * gridDim.y + h) * gridDim.x + rt) * 24 : nullptr;
   const bool masked = p.row_id != nullptr;
   const int n_col_tiles = (p.S_col + kCols - 1) / kCols;
   const int n_row_tiles64 = (p.S_row + 63) / 64;
-
-  // label range of the resident rows (two 64-token range entries)
-  int row_lo = 0, row_hi = 0;
-  if (masked) {
-    const int i0 = rt * 2, i1 = min(rt * 2 + 1, n_row_tiles64 - 1);
-    row_lo = min(p.row_min[b * n_row_tiles64 + i0], p.row_min[b * n_row_tiles64 + i1]);
-    row_hi = max(p.row_max[b * n_row_tiles64 + i0], p.row_max[b * n_row_tiles64 + i1]);
-  }
+  const int n_row_tiles = (p.S_row + kRows - 1) / kRows;
+  const int n_items = n_row_tiles * p.H * p.B;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_resA); tma_prefetch_desc(&tm_resB); tma_prefetch_desc(&tm_stA);
@@ -214,17 +208,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (warp == 3) {
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- persistent loop over work items (row tile, head, batch): barriers, TMEM and the smem rings live across items,
+  //      which removes the 1-1.6 us launch gap between consecutive CTAs of an SM and the per-CTA setup.  All barrier
+  //      parities below run on counters that continue across items (`base` = streamed tiles of the earlier items). ----
+  int base = 0;                 // streamed tiles consumed by earlier items of this CTA
+  uint32_t item_n = 0;          // items done by this CTA (parity of the once-per-item barriers)
+  int pstage = 0;               // producer ring position (continues across items)
+  uint32_t pphase = 0;
+  // dynamic hand-out (items differ a lot in their number of visible tiles).  Warp 2, idle after the TMEM allocation,
+  // works one item ahead: it fetches the id of the next item and builds that item's list of visible tiles while the
+  // current item runs, so neither the atomic's round trip nor the list build is on anybody's critical path.
+  auto build_list = [&](int it, int buf) {       // whole warp
+    const int rt_ = it % n_row_tiles, b_ = it / (n_row_tiles * p.H);
+    uint16_t* list = tile_lists + buf * kMaxTiles;
+    // label range of the resident rows (two 64-token range entries)
+    int row_lo = 0, row_hi = 0;
+    if (masked) {
+      const int i0 = rt_ * 2, i1 = min(rt_ * 2 + 1, n_row_tiles64 - 1);
+      row_lo = min(p.row_min[b_ * n_row_tiles64 + i0], p.row_min[b_ * n_row_tiles64 + i1]);
+      row_hi = max(p.row_max[b_ * n_row_tiles64 + i0], p.row_max[b_ * n_row_tiles64 + i1]);
+    }
     // visible streamed tiles, in order (DKV: q tiles with qmax >= kmin(rows); DQ: k tiles with kmin <= qmax(rows)).
     // bit 15 of an entry = the tile needs the per-element label compare (it straddles a label boundary, or it is
     // the ragged tail of the key axis), so the compute warps never touch the range arrays in global memory.
     int cnt = 0;
-    for (int base = 0; base < n_col_tiles; base += 32) {
-      const int t = base + lane;
+    for (int cb = 0; cb < n_col_tiles; cb += 32) {
+      const int t = cb + lane;
       bool vis = t < n_col_tiles, nm = false;
       if (vis) {
         int cmin = 0, cmax = 0;
-        if (masked) { cmin = p.col_min[b * n_col_tiles + t]; cmax = p.col_max[b * n_col_tiles + t]; }
+        if (masked) { cmin = p.col_min[b_ * n_col_tiles + t]; cmax = p.col_max[b_ * n_col_tiles + t]; }
         if (MODE == MODE_DKV) {
           vis = !masked || cmax >= row_lo;
           nm = masked && (row_hi > cmin);
@@ -234,17 +252,37 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, vis);
-      if (vis) tile_list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(t | (nm ? 0x8000 : 0));
+      if (vis) list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(t | (nm ? 0x8000 : 0));
       cnt += __popc(m);
     }
-    if (lane == 0) *n_tiles_slot = cnt;
+    if (lane == 0) n_tiles_slot[buf] = cnt;
+  };
+  if (warp == 2) {
+    int first = 0;
+    if (lane == 0) first = static_cast<int>(atomicAdd(&g_bwd_items[MODE][0], 1u));
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (lane == 0) item_slot[0] = first;
+    if (first < n_items) build_list(first, 0);
   }
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int T = *n_tiles_slot;
+  for (int item = item_slot[0]; item < n_items; item = item_slot[(item_n + 1) & 1], ++item_n) {
+  const int rt = item % n_row_tiles, h = (item / n_row_tiles) % p.H, b = item / (n_row_tiles * p.H);
+  const int r0 = rt * kRows;
+  const long long t_start = kProf ? clock64() : 0;
+  unsigned long long g_start = 0;
+  if (kProf == 2 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
+  long long* prof = kProf ? p.prof + static_cast<long long>(item) * 24 : nullptr;
+  const uint16_t* tile_list = tile_lists + (item_n & 1) * kMaxTiles;     // made visible by the previous item's final barrier
+  const int T = n_tiles_slot[item_n & 1];
   if (kFull && threadIdx.x == 0) { prof[1] = clock64() - t_start; prof[2] = T; }
+
+  if (warp == 2) {
+    int nxt = 0;
+    if (lane == 0) nxt = static_cast<int>(atomicAdd(&g_bwd_items[MODE][0], 1u));
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    if (lane == 0) item_slot[(item_n + 1) & 1] = nxt;
+    if (nxt < n_items) build_list(nxt, (item_n + 1) & 1);
+  }
 
   constexpr uint32_t kStageBytes = (MODE == MODE_DKV) ? 16384u : 12288u;
 
@@ -262,24 +300,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         tma_load_4d(smem + TcSmem::resB, &tm_resB, res_full, 0, h, r0, b);
       }
       __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
       long long w_se = 0;
       for (int j = 0; j < T_u; ++j) {
         const int t = __shfl_sync(0xffffffffu, tile_list[j] & 0x7fff, 0);
-        uint8_t* st = smem + TcSmem::stream + stage * 16384;
-        wait_acc<kProf>(&st_empty[stage], phase ^ 1, w_se);
+        uint8_t* st = smem + TcSmem::stream + pstage * 16384;
+        wait_acc<kProf>(&st_empty[pstage], pphase ^ 1, w_se);
         if (elect_one()) {
-          mbar_expect_tx(&st_full[stage], p.mn_major ? 8192u : kStageBytes);
-          tma_load_4d(st, &tm_stA, &st_full[stage], 0, h, t * kCols, b);
-          tma_load_4d(st + 4096, &tm_stB, &st_full[stage], 0, h, t * kCols, b);
+          mbar_expect_tx(&st_full[pstage], p.mn_major ? 8192u : kStageBytes);
+          tma_load_4d(st, &tm_stA, &st_full[pstage], 0, h, t * kCols, b);
+          tma_load_4d(st + 4096, &tm_stB, &st_full[pstage], 0, h, t * kCols, b);
           if (!p.mn_major) {
-            if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[stage], t * kCols, (b * p.H + h) * 32);
-            tma_load_2d(st + 12288, &tm_tB, &st_full[stage], t * kCols, (b * p.H + h) * 32);
+            if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[pstage], t * kCols, (b * p.H + h) * 32);
+            tma_load_2d(st + 12288, &tm_tB, &st_full[pstage], t * kCols, (b * p.H + h) * 32);
           }
         }
         __syncwarp();
-        if (++stage == kNST) { stage = 0; phase ^= 1; }
+        if (++pstage == kNST) { pstage = 0; pphase ^= 1; }
       }
       if (kFull && lane == 0) prof[14] = w_se;
     }
@@ -294,12 +330,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t dA = umma_desc_sw64(smem_u32(smem + TcSmem::resA)), dB = umma_desc_sw64(smem_u32(smem + TcSmem::resB));
       const uint32_t stream = smem_u32(smem + TcSmem::stream);
-      mbar_wait(res_full, 0);
+      mbar_wait(res_full, item_n & 1);
       tc_fence_after();
       long long w_sf = 0, w_free = 0;
       for (int js = 0; js < T_u; ++js) {
-        const int stage = js % kNST, g = js % kNG, n = js / kNG;
-        wait_acc<kProf>(&st_full[stage], (js / kNST) & 1, w_sf);
+        const int gt = base + js;                    // tile counter across items
+        const int stage = gt % kNST, g = gt % kNG, n = gt / kNG;
+        wait_acc<kProf>(&st_full[stage], (gt / kNST) & 1, w_sf);
         wait_acc<kProf>(&stage_free[g], (n & 1) ^ 1, w_free);
         tc_fence_after();
         const uint64_t dS = umma_desc_sw64(stream + stage * 16384), dD = umma_desc_sw64(stream + stage * 16384 + 4096);
@@ -324,7 +361,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       const uint32_t stream = smem_u32(smem + TcSmem::stream);
       long long w_pr = 0;
       for (int ia = 0; ia < T_u; ++ia) {
-        const int stage = ia % kNST, g = ia % kNG, n = ia / kNG;
+        const int gt = base + ia;                    // tile counter across items
+        const int stage = gt % kNST, g = gt % kNG, n = gt / kNG;
         wait_acc<kProf>(&p_ready[g], n & 1, w_pr);
         tc_fence_after();
         const uint32_t ta = tmem_u + g * 128;             // P pairs at +0..31, dS pairs at +64..95 (written in place)
@@ -397,11 +435,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         pre_i = ok ? (masked ? p.col_id[static_cast<long long>(b) * p.S_col + c] : 0) : 0x7fffffff;
       }
     };
-    prefetch(g);
+    const int j0 = (g + kNG - base % kNG) % kNG;      // first tile of this item that belongs to stage g
+    prefetch(j0);
     long long w_full = 0, w_bar = 0, w_comp = 0;
     const bool prof_me = kFull && warp == 4 && lane == 0;
-    for (int j = g; j < T; j += kNG) {
-      const int n = j / kNG;
+    for (int j = j0; j < T; j += kNG) {
+      const int n = (base + j) / kNG;                  // use count of stage g across items
       const bool need_mask = (tile_list[j] & 0x8000) != 0;
       // column statistics: double buffered per warpgroup, so one barrier per tile (write -> barrier -> read; the
       // previous tile's readers use the other buffer)
@@ -418,7 +457,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       if (kFull) w_bar += clock64() - tb0;
       prefetch(j + kNG);
       wait_acc<kProf>(&sdp_full[g], n & 1, w_full);
-      if (prof_me && j == 0) prof[3] = clock64() - t_start;
+      if (prof_me && j == j0) prof[3] = clock64() - t_start;
       const long long tc0 = kFull ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + g * 128;
@@ -501,7 +540,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     }
     if (prof_me) { prof[4] = w_full; prof[6] = w_bar; prof[7] = w_comp; prof[8] = clock64() - t_start; }
     // ---- epilogue: accumulators -> bf16 -> global ----
-    mbar_wait(acc_full, 0);
+    mbar_wait(acc_full, item_n & 1);
     if (prof_me) prof[9] = clock64() - t_start;
     tc_fence_after();
     const bool writes = (MODE == MODE_DKV) ? (g < 2) : (g == 1);     // warp-uniform: wg0 -> acc0 (dV), wg1 -> acc1 (dK / dQ)
@@ -532,12 +571,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     if (prof_me) prof[10] = clock64() - t_start;
   }
 
+  // ---- end of the item: every role has drained (accumulators read, all MMAs retired, tile list no longer needed) ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
+  tc_fence_after();
+  base += T;
   if (kProf && threadIdx.x == 0) {
     prof[0] = clock64() - t_start;
     if (kProf == 2) {
@@ -546,6 +584,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       prof[20] = static_cast<long long>(g_start); prof[21] = static_cast<long long>(g_end); prof[22] = smid; prof[2] = T;
+    }
+  }
+  }   // item loop
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) {
+    // the last CTA out re-arms the hand-out for the next launch
+    if (atomicAdd(&g_bwd_items[MODE][1], 1u) == gridDim.x - 1) {
+      g_bwd_items[MODE][0] = 0u;
+      g_bwd_items[MODE][1] = 0u;
+      __threadfence();
     }
   }
 }
@@ -988,6 +1042,16 @@ FK_API int fk_attn_transpose(const void* x, long long bs, long long ts, int B, i
   return FK_OK;
 }
 
+static int bwd_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
 // Diagnosis only: route fk_attn_backward_tc to the stall-accounting instantiation (prof: int64 [n_ctas, 16]; null = off).
 FK_API int fk_attn_set_profile_buffer(long long* prof, int mode) {
   g_attn_prof = prof;
@@ -1050,7 +1114,10 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
   FK_REQUIRE(!(parts & 2) || (dk && dv), "fk_attn_backward_tc: dK/dV needs dk, dv");
   FK_REQUIRE(!(parts & 4) || dq, "fk_attn_backward_tc: dQ needs dq");
   if (rc != 0) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
-  const dim3 grid((S + kRows - 1) / kRows, H, B);
+  // persistent CTAs: one per SM (or per work item when there are fewer), looping over (row tile, head, batch) items
+  const long long n_items = static_cast<long long>((S + kRows - 1) / kRows) * H * B;
+  FK_REQUIRE(n_items < (1ll << 31), "fk_attn_backward_tc: too many work items");
+  const dim3 grid(static_cast<unsigned>(n_items < bwd_sm_count() ? n_items : bwd_sm_count()), 1, 1);
   int n = 0;
   if (parts & 2) {
     TcParams p = {};
