@@ -74,9 +74,9 @@ __device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t phase, long lon
 
 struct TcSmem {
   // offsets from the 1024-aligned dynamic smem base
-  static constexpr int resA = 0;                       // 128 x 64 B
+  static constexpr int resA = 0;                       // 128 x 64 B; second buffer (next item, prefetched) at + 16384
   static constexpr int resB = 8192;
-  static constexpr int stream = 16384;                 // kNST x 16 KB: stA | stB | tA | tB (4 KB each)
+  static constexpr int stream = 32768;                 // kNST x 16 KB: stA | stB | tA | tB (4 KB each)
   static constexpr int stats = stream + kNST * 16384;  // [2 wg][2 buffers][lse | delta | id][64] x 4 B           // [2 wg][lse | delta | id][64] x 4 B
   static constexpr int tiles = stats + kNG * 2 * 3 * 64 * 4; // uint16 visible-tile list
   static constexpr int bars = tiles + 2 * kMaxTiles * 2;   // two lists: the next item's is built while this one runs
@@ -168,10 +168,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);
-  uint64_t* res_full = bars;               // [1]
-  uint64_t* st_full = bars + 1;            // [kNST]
-  uint64_t* st_empty = bars + 1 + kNST;    // [kNST]
-  uint64_t* sdp_full = bars + 1 + 2 * kNST;   // [kNG]  score stage g written by the tensor core
+  uint64_t* res_full = bars;               // [2]    resident tiles of item n in buffer n & 1
+  uint64_t* list_ready = bars + 2;         // [1]    warp 2 has written the id and the tile list of the next item
+  uint64_t* st_full = bars + 3;            // [kNST]
+  uint64_t* st_empty = bars + 3 + kNST;    // [kNST]
+  uint64_t* sdp_full = bars + 3 + 2 * kNST;   // [kNG]  score stage g written by the tensor core
   uint64_t* stage_free = sdp_full + kNG;   // [kNG]  the accumulate MMAs that read stage g (as P / dS) have retired
   uint64_t* p_ready = stage_free + kNG;    // [kNG]  P / dS written in place into stage g (4 warps arrive)
   uint64_t* acc_full = p_ready + kNG;      // [1]
@@ -194,7 +195,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     if (MODE == MODE_DKV) tma_prefetch_desc(&tm_tA);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(res_full, 1);
+    mbar_init(&res_full[0], 1);
+    mbar_init(&res_full[1], 1);
+    mbar_init(list_ready, 1);
     for (int i = 0; i < kNST; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
     for (int i = 0; i < kNG; ++i) {
       mbar_init(&sdp_full[i], 1);
@@ -220,6 +223,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   uint32_t item_n = 0;          // items done by this CTA (parity of the once-per-item barriers)
   int pstage = 0;               // producer ring position (continues across items)
   uint32_t pphase = 0;
+  int pre_cnt = -1;             // producer: streamed tiles of THIS item already requested during the previous item
+                                // (-1: nothing, not even the resident tiles)
   // dynamic hand-out (items differ a lot in their number of visible tiles).  Warp 2, idle after the TMEM allocation,
   // works one item ahead: it fetches the id of the next item and builds that item's list of visible tiles while the
   // current item runs, so neither the atomic's round trip nor the list build is on anybody's critical path.
@@ -282,6 +287,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     nxt = __shfl_sync(0xffffffffu, nxt, 0);
     if (lane == 0) item_slot[(item_n + 1) & 1] = nxt;
     if (nxt < n_items) build_list(nxt, (item_n + 1) & 1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(list_ready);      // phase item_n: the producer may now run ahead into the next item
   }
 
   constexpr uint32_t kStageBytes = (MODE == MODE_DKV) ? 16384u : 12288u;
@@ -294,28 +301,46 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     // waterfall (ELECT + R2UR.BROADCAST chain + branch, ~115 cycles per MMA issue -- scripts/gpu_search_stalls.py).
     {
       const int T_u = __shfl_sync(0xffffffffu, T, 0);
-      if (elect_one()) {
-        mbar_expect_tx(res_full, 16384);
-        tma_load_4d(smem + TcSmem::resA, &tm_resA, res_full, 0, h, r0, b);
-        tma_load_4d(smem + TcSmem::resB, &tm_resB, res_full, 0, h, r0, b);
-      }
-      __syncwarp();
       long long w_se = 0;
-      for (int j = 0; j < T_u; ++j) {
-        const int t = __shfl_sync(0xffffffffu, tile_list[j] & 0x7fff, 0);
+      auto load_resident = [&](int h_, int r0_, int b_, int buf) {
+        if (elect_one()) {
+          mbar_expect_tx(&res_full[buf], 16384);
+          tma_load_4d(smem + TcSmem::resA + buf * 16384, &tm_resA, &res_full[buf], 0, h_, r0_, b_);
+          tma_load_4d(smem + TcSmem::resB + buf * 16384, &tm_resB, &res_full[buf], 0, h_, r0_, b_);
+        }
+        __syncwarp();
+      };
+      auto load_tile = [&](int t, int h_, int b_) {
         uint8_t* st = smem + TcSmem::stream + pstage * 16384;
         wait_acc<kProf>(&st_empty[pstage], pphase ^ 1, w_se);
         if (elect_one()) {
           mbar_expect_tx(&st_full[pstage], p.mn_major ? 8192u : kStageBytes);
-          tma_load_4d(st, &tm_stA, &st_full[pstage], 0, h, t * kCols, b);
-          tma_load_4d(st + 4096, &tm_stB, &st_full[pstage], 0, h, t * kCols, b);
+          tma_load_4d(st, &tm_stA, &st_full[pstage], 0, h_, t * kCols, b_);
+          tma_load_4d(st + 4096, &tm_stB, &st_full[pstage], 0, h_, t * kCols, b_);
           if (!p.mn_major) {
-            if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[pstage], t * kCols, (b * p.H + h) * 32);
-            tma_load_2d(st + 12288, &tm_tB, &st_full[pstage], t * kCols, (b * p.H + h) * 32);
+            if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[pstage], t * kCols, (b_ * p.H + h_) * 32);
+            tma_load_2d(st + 12288, &tm_tB, &st_full[pstage], t * kCols, (b_ * p.H + h_) * 32);
           }
         }
         __syncwarp();
         if (++pstage == kNST) { pstage = 0; pphase ^= 1; }
+      };
+      // this item: whatever the previous item's run-ahead has not requested yet
+      if (pre_cnt < 0) { load_resident(h, r0, b, item_n & 1); pre_cnt = 0; }
+      for (int j = pre_cnt; j < T_u; ++j) load_tile(__shfl_sync(0xffffffffu, tile_list[j] & 0x7fff, 0), h, b);
+      // run ahead into the next item while this one drains: its resident tiles (other buffer) and as many of its first
+      // streamed tiles as the ring takes without waiting on this item's last consumers for long (half the ring)
+      mbar_wait(list_ready, item_n & 1);
+      const int nxt = __shfl_sync(0xffffffffu, item_slot[(item_n + 1) & 1], 0);
+      pre_cnt = -1;
+      if (nxt < n_items) {
+        const int rt2 = nxt % n_row_tiles, h2 = (nxt / n_row_tiles) % p.H, b2 = nxt / (n_row_tiles * p.H);
+        const uint16_t* list2 = tile_lists + ((item_n + 1) & 1) * kMaxTiles;
+        const int T2 = __shfl_sync(0xffffffffu, n_tiles_slot[(item_n + 1) & 1], 0);
+        load_resident(h2, rt2 * kRows, b2, (item_n + 1) & 1);
+        pre_cnt = 0;
+        const int ahead = T2 < kNST / 2 ? T2 : kNST / 2;
+        for (int j = 0; j < ahead; ++j, ++pre_cnt) load_tile(__shfl_sync(0xffffffffu, list2[j] & 0x7fff, 0), h2, b2);
       }
       if (kFull && lane == 0) prof[14] = w_se;
     }
@@ -328,9 +353,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       constexpr uint32_t idesc_score = umma_idesc_bf16(kRows, kCols);
       const int T_u = __shfl_sync(0xffffffffu, T, 0);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint64_t dA = umma_desc_sw64(smem_u32(smem + TcSmem::resA)), dB = umma_desc_sw64(smem_u32(smem + TcSmem::resB));
+      const uint64_t dA = umma_desc_sw64(smem_u32(smem + TcSmem::resA + (item_n & 1) * 16384)),
+                     dB = umma_desc_sw64(smem_u32(smem + TcSmem::resB + (item_n & 1) * 16384));
       const uint32_t stream = smem_u32(smem + TcSmem::stream);
-      mbar_wait(res_full, item_n & 1);
+      mbar_wait(&res_full[item_n & 1], (item_n >> 1) & 1);
       tc_fence_after();
       long long w_sf = 0, w_free = 0;
       for (int js = 0; js < T_u; ++js) {
