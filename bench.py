@@ -38,8 +38,8 @@ CPU_SAMPLE_TRIALS = 2
 # (attention rows: the capture in profiles/r01_attention_tc_ncu_full.txt is a 16-trial launch; trials are independent,
 #  so a B-trial launch moves B/16 times those bytes)
 NCU_TRAFFIC = {"vq_search": 12660224}
-NCU_TRAFFIC_PER_16_TRIALS = {"attn_fwd": 201665792 + 54162944, "attn_bwd_dkv": 411375872 + 119109888,
-                             "attn_bwd_dq": 344237568 + 61068800}
+NCU_TRAFFIC_PER_16_TRIALS = {"attn_fwd": 201729792 + 55561984, "attn_bwd_dkv": 277267200 + 111549184,
+                             "attn_bwd_dq": 277148928 + 56863744}
 
 
 def model_configs():
