@@ -146,7 +146,10 @@ int fk_attn_set_profile_buffer(long long* prof, int mode);   /* mode 1 = full st
  * contractions over tokens read the Q / dO / K tiles MN-major straight from the strided inputs.  Cross-check mode:
  * fk_attn_transpose makes [B][H][32][Sp] copies (zero padded, Sp % 8 == 0) that serve as K-major operands instead:
  * qt, dot for dK/dV (parts & 2), kt for dQ (parts & 4).  delta must already hold rowsum(dO*O)
- * (fk_attn_backward with parts = 1).  Same labels / ranges / strides conventions as fk_attn_backward; Sq == Sk == S. */
+ * (fk_attn_backward with parts = 1).  Same labels / ranges / strides conventions as fk_attn_backward; Sq == Sk == S.
+ * The kernels are persistent (one CTA per SM taking work items from a device-side counter that re-arms itself at the end
+ * of a launch): like the rest of this ABI they are meant to be driven from ONE stream per process; two launches of the
+ * same part running concurrently on different streams would share the counter. */
 int fk_attn_transpose(const void* x, long long bs, long long ts, int B, int S, int H, int head_dim, void* xt, int Sp,
                       void* stream);
 int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
