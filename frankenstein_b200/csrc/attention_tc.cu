@@ -676,8 +676,9 @@ attn_transpose_kernel(const __nv_bfloat16* __restrict__ x, long long bs, long lo
 constexpr int kFwdTileK = 128;
 constexpr int kFwdThreads = 384;
 constexpr float kRescaleSlack = 8.f;
-// an optimistic sweep whose scores exceed the stale reference by more than 2^kRedoExcess is redone with the true maximum
-constexpr float kRedoExcess = 60.f;
+// an optimistic sweep whose row sum exceeds this has met scores above its stale reference (every 2^(s - m) <= 1 sums to
+// at most 128): the tile is redone with its true maximum
+constexpr float kStaleSum = 256.f;
 
 struct FwdSmem {
   static constexpr int q = 0;                           // 2 x 128 x 64 B
@@ -912,9 +913,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           alpha_pend = 1.f;
         }
       };
-      // one sweep over the 128 scores of this row: P = 2^(S c - m_use) -> bf16 pairs into the operand buffer, row sum,
-      // and the raw row maximum on the side; TMEM loads double buffered.  `first_loaded`: chunk 0 is already in flight.
-      float rs = 0.f, mx = -INFINITY;
+      // one sweep over the 128 scores of this row: P = 2^(S c - m_use) -> bf16 pairs into the operand buffer and the row
+      // sum; TMEM loads double buffered.  The optimistic sweep does not even track the row maximum (one instruction per
+      // score less): a reference that has gone stale shows up in the row sum instead -- sum > kStaleSum means some
+      // 2^(s - m) > 2, +inf means overflow -- and only then is the tile redone with its true maximum.
+      float rs = 0.f;
       bool released = false, redo = false;
       auto release_scores = [&]() {                      // S_g fully consumed: the next tile's scores may land
         tc_fence_before();
@@ -924,7 +927,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       };
       auto exp_sweep = [&](float m_use, bool optimistic) {
         rs = 0.f;
-        mx = -INFINITY;
         if (optimistic) tmem_ld32(s_addr, sv[0]);        // (otherwise chunk 0 was requested by the maximum pass)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -932,15 +934,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tmem_wait1_32(sv[cur]);
           if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, sv[cur ^ 1]);
           mask_chunk(sv[cur], c);
-          if (optimistic) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[cur][i]), __uint_as_float(sv[cur][i + 1])));
-          }
-          if (c == 3) {
-            // every score is in registers; the optimistic sweep first checks that its stale reference was safe
-            if (optimistic) redo = __any_sync(0xffffffffu, mx * p.scale_log2 > m_run + kRedoExcess);
-            if (!redo) release_scores();
-          }
+          if (c == 3 && !optimistic) release_scores();   // every score is in registers and no redo can follow
           uint32_t pw[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -963,15 +957,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // ---- optimistic single sweep against the stale running maximum (softmax is shift invariant; the reference
         //      only has to keep 2^(s - m) inside the fp32 / bf16 exponent range) ----
         exp_sweep(m_run, true);
-        const float m_tile = mx * p.scale_log2;
+        redo = __any_sync(0xffffffffu, !(rs <= kStaleSum));        // (also true for +inf / NaN)
         if (!redo) {
+          release_scores();
           l_run += rs;
-          if (m_tile > m_run + kRescaleSlack) {          // lazy: raise the reference for the tiles to come
-            const float a = fast_ex2(m_run - m_tile);
-            l_run *= a;
-            alpha_pend = a;                              // applied to O_g after this tile's P V MMAs
-            m_run = m_tile;
-          }
         }
       }
       if (two_pass || redo) {
@@ -989,7 +978,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           for (int i = 0; i < 32; i += 2) mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[cur][i]), __uint_as_float(sv[cur][i + 1])));
         }
         const float m_tile = mx1 * p.scale_log2;
-        const bool raise = m_tile > m_run + kRescaleSlack || m_run == -INFINITY;
+        // (after a stale-reference redo every increase is taken, otherwise the next tile would trip the same check)
+        const bool raise = m_tile > m_run + (redo ? 0.f : kRescaleSlack) || m_run == -INFINITY;
         const float m_new = raise ? fmaxf(m_run, m_tile) : m_run;
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
         const float alpha = (raise && m_run != -INFINITY) ? fast_ex2(m_run - m_use) : 1.f;
