@@ -681,13 +681,15 @@ constexpr float kRescaleSlack = 8.f;
 constexpr float kStaleSum = 256.f;
 
 struct FwdSmem {
-  static constexpr int q = 0;                           // 2 x 128 x 64 B
-  static constexpr int stream = 16384;                  // kNST x 16 KB: K (8 KB) | Vt slab 0 | Vt slab 1 (4 KB each)
+  static constexpr int q = 0;                           // 2 buffers (item n in buffer n & 1) x 2 groups x 128 x 64 B
+  static constexpr int stream = 32768;                  // kNST x 16 KB: K tile (8 KB) | V tile (8 KB)
   static constexpr int ids = stream + kNST * 16384;     // [2 wg][2 buffers][128] int
   static constexpr int tiles = ids + 2 * 2 * 128 * 4;
-  static constexpr int bars = tiles + kMaxTiles * 2;
+  static constexpr int bars = tiles + 2 * kMaxTiles * 2;     // two lists: the next item's is built while this one runs
   static constexpr int total = bars + 256;
 };
+
+__device__ unsigned int g_fwd_items[2];      // [0] next item, [1] CTAs finished (see g_bwd_items)
 
 struct FwdParams {
   const int *qid, *kid;
@@ -705,38 +707,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
-  uint64_t* q_full = bars;                  // [1]
-  uint64_t* st_full = bars + 1;             // [kNST]
+  uint64_t* q_full = bars;                  // [2]     Q tiles of item n in buffer n & 1
+  uint64_t* list_ready = bars + 2;          // [1]     warp 2 has written the id and the tile list of the next item
+  uint64_t* st_full = bars + 3;             // [kNST]
   uint64_t* st_empty = st_full + kNST;      // [kNST]  two arrivals: the P V MMAs of both warpgroups
   uint64_t* s_full = st_empty + kNST;       // [2]     S_g written by the tensor core
   uint64_t* s_free = s_full + 2;            // [2]     S_g read out (4 warps)
   uint64_t* p_ready = s_free + 2;           // [2]     P_g written (4 warps)
   uint64_t* p_free = p_ready + 2;           // [2]     P V MMAs of warpgroup g retired (O_g quiescent, P_g reusable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
-  int* n_tiles_slot = reinterpret_cast<int*>(p_free + 2) + 1;
-  uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem + FwdSmem::tiles);
+  int* n_tiles_slot = reinterpret_cast<int*>(p_free + 2) + 1;   // [2]
+  int* item_slot = reinterpret_cast<int*>(p_free + 2) + 3;      // [2]
+  uint16_t* tile_lists = reinterpret_cast<uint16_t*>(smem + FwdSmem::tiles);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qt * 256;
   const bool masked = p.qid != nullptr;
   const int n_k_tiles = (p.Sk + kFwdTileK - 1) / kFwdTileK;
   const int nq64 = (p.Sq + 63) / 64, nk64 = (p.Sk + 63) / 64;
-
-  // label ranges of the two warpgroups' rows (two 64-row entries each)
-  int wq_lo[2] = {0, 0}, wq_hi[2] = {0, 0};
-  if (masked) {
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int i0 = min(qt * 4 + g * 2, nq64 - 1), i1 = min(qt * 4 + g * 2 + 1, nq64 - 1);
-      wq_lo[g] = min(p.qmin[b * nq64 + i0], p.qmin[b * nq64 + i1]);
-      wq_hi[g] = max(p.qmax[b * nq64 + i0], p.qmax[b * nq64 + i1]);
-    }
-  }
+  const int n_q_tiles = (p.Sq + 255) / 256;
+  const int n_items = n_q_tiles * p.H * p.B;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(list_ready, 1);
     for (int i = 0; i < kNST; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 2); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -750,20 +745,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (warp == 3) {
-    // key tiles visible to at least one of the CTA's rows; bits 14 / 15 = warpgroup 0 / 1 must compare labels
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // key tiles visible to at least one of the item's rows; bits 14 / 15 = warpgroup 0 / 1 must compare labels
+  auto build_list = [&](int it, int buf) {       // whole warp
+    const int qt_ = it % n_q_tiles, b_ = it / (n_q_tiles * p.H);
+    uint16_t* list = tile_lists + buf * kMaxTiles;
+    // label ranges of the two warpgroups' rows (two 64-row entries each)
+    int wq_lo[2] = {0, 0}, wq_hi[2] = {0, 0};
+    if (masked) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int i0 = min(qt_ * 4 + g * 2, nq64 - 1), i1 = min(qt_ * 4 + g * 2 + 1, nq64 - 1);
+        wq_lo[g] = min(p.qmin[b_ * nq64 + i0], p.qmin[b_ * nq64 + i1]);
+        wq_hi[g] = max(p.qmax[b_ * nq64 + i0], p.qmax[b_ * nq64 + i1]);
+      }
+    }
     const int cta_hi = max(wq_hi[0], wq_hi[1]);
     int cnt = 0;
-    for (int base = 0; base < n_k_tiles; base += 32) {
-      const int t = base + lane;
+    for (int cb = 0; cb < n_k_tiles; cb += 32) {
+      const int t = cb + lane;
       bool vis = t < n_k_tiles;
       int flags = 0;
       if (vis) {
         int kmn = 0, kmx = 0;
         if (masked) {
           const int i0 = min(t * 2, nk64 - 1), i1 = min(t * 2 + 1, nk64 - 1);
-          kmn = min(p.kmin[b * nk64 + i0], p.kmin[b * nk64 + i1]);
-          kmx = max(p.kmax[b * nk64 + i0], p.kmax[b * nk64 + i1]);
+          kmn = min(p.kmin[b_ * nk64 + i0], p.kmin[b_ * nk64 + i1]);
+          kmx = max(p.kmax[b_ * nk64 + i0], p.kmax[b_ * nk64 + i1]);
           vis = kmn <= cta_hi;
         }
         const bool tail = t * kFwdTileK + kFwdTileK > p.Sk;
@@ -771,41 +783,82 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if ((masked && kmx > wq_lo[1]) || tail) flags |= 0x8000;
       }
       const unsigned m = __ballot_sync(0xffffffffu, vis);
-      if (vis) tile_list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(t | flags);
+      if (vis) list[cnt + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(t | flags);
       cnt += __popc(m);
     }
-    if (lane == 0) *n_tiles_slot = cnt;
+    if (lane == 0) n_tiles_slot[buf] = cnt;
+  };
+
+  // ---- persistent loop over work items (256-query block, head, trial), as in the backward kernel: dynamic hand-out,
+  //      warp 2 prepares the next item's id and tile list one item ahead, the producer runs ahead into the next item,
+  //      barrier parities run on counters that continue across items (`base` = key tiles of the earlier items) ----
+  int base = 0;
+  uint32_t item_n = 0;
+  int pstage = 0;
+  uint32_t pphase = 0;
+  int pre_cnt = -1;
+  if (warp == 2) {
+    int first = 0;
+    if (lane == 0) first = static_cast<int>(atomicAdd(&g_fwd_items[0], 1u));
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (lane == 0) item_slot[0] = first;
+    if (first < n_items) build_list(first, 0);
   }
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int T = *n_tiles_slot;
+  for (int item = item_slot[0]; item < n_items; item = item_slot[(item_n + 1) & 1], ++item_n) {
+  const int qt = item % n_q_tiles, h = (item / n_q_tiles) % p.H, b = item / (n_q_tiles * p.H);
+  const int q0 = qt * 256;
+  const uint16_t* tile_list = tile_lists + (item_n & 1) * kMaxTiles;
+  const int T = n_tiles_slot[item_n & 1];
+
+  if (warp == 2) {
+    int nxt = 0;
+    if (lane == 0) nxt = static_cast<int>(atomicAdd(&g_fwd_items[0], 1u));
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    if (lane == 0) item_slot[(item_n + 1) & 1] = nxt;
+    if (nxt < n_items) build_list(nxt, (item_n + 1) & 1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(list_ready);
+  }
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     // (whole-warp loops with one elected issuing lane: see the backward kernel)
     {
       const int T_u = __shfl_sync(0xffffffffu, T, 0);
-      if (elect_one()) {
-        mbar_expect_tx(q_full, 16384);
-        tma_load_4d(smem + FwdSmem::q, &tm_q, q_full, 0, h, q0, b);
-        tma_load_4d(smem + FwdSmem::q + 8192, &tm_q, q_full, 0, h, q0 + 128, b);
-      }
-      __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < T_u; ++j) {
-        const int t = __shfl_sync(0xffffffffu, tile_list[j] & 0x3fff, 0);
-        uint8_t* st = smem + FwdSmem::stream + stage * 16384;
-        mbar_wait(&st_empty[stage], phase ^ 1);
+      auto load_q = [&](int h_, int q0_, int b_, int buf) {
         if (elect_one()) {
-          mbar_expect_tx(&st_full[stage], 16384);
-          tma_load_4d(st, &tm_k, &st_full[stage], 0, h, t * kFwdTileK, b);
-          tma_load_4d(st + 8192, &tm_v, &st_full[stage], 0, h, t * kFwdTileK, b);      // V tile [128 keys][32 dims]
+          mbar_expect_tx(&q_full[buf], 16384);
+          tma_load_4d(smem + FwdSmem::q + buf * 16384, &tm_q, &q_full[buf], 0, h_, q0_, b_);
+          tma_load_4d(smem + FwdSmem::q + buf * 16384 + 8192, &tm_q, &q_full[buf], 0, h_, q0_ + 128, b_);
         }
         __syncwarp();
-        if (++stage == kNST) { stage = 0; phase ^= 1; }
+      };
+      auto load_tile = [&](int t, int h_, int b_) {
+        uint8_t* st = smem + FwdSmem::stream + pstage * 16384;
+        mbar_wait(&st_empty[pstage], pphase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&st_full[pstage], 16384);
+          tma_load_4d(st, &tm_k, &st_full[pstage], 0, h_, t * kFwdTileK, b_);
+          tma_load_4d(st + 8192, &tm_v, &st_full[pstage], 0, h_, t * kFwdTileK, b_);      // V tile [128 keys][32 dims]
+        }
+        __syncwarp();
+        if (++pstage == kNST) { pstage = 0; pphase ^= 1; }
+      };
+      if (pre_cnt < 0) { load_q(h, q0, b, item_n & 1); pre_cnt = 0; }
+      for (int j = pre_cnt; j < T_u; ++j) load_tile(__shfl_sync(0xffffffffu, tile_list[j] & 0x3fff, 0), h, b);
+      // run ahead into the next item while this one drains
+      mbar_wait(list_ready, item_n & 1);
+      const int nxt = __shfl_sync(0xffffffffu, item_slot[(item_n + 1) & 1], 0);
+      pre_cnt = -1;
+      if (nxt < n_items) {
+        const int qt2 = nxt % n_q_tiles, h2 = (nxt / n_q_tiles) % p.H, b2 = nxt / (n_q_tiles * p.H);
+        const uint16_t* list2 = tile_lists + ((item_n + 1) & 1) * kMaxTiles;
+        const int T2 = __shfl_sync(0xffffffffu, n_tiles_slot[(item_n + 1) & 1], 0);
+        load_q(h2, qt2 * 256, b2, (item_n + 1) & 1);
+        pre_cnt = 0;
+        const int ahead = T2 < kNST / 2 ? T2 : kNST / 2;
+        for (int j = 0; j < ahead; ++j, ++pre_cnt) load_tile(__shfl_sync(0xffffffffu, list2[j] & 0x3fff, 0), h2, b2);
       }
     }
   } else if (warp == 1) {
@@ -814,17 +867,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       constexpr uint32_t idesc = umma_idesc_bf16(128, kFwdTileK);
       const int T_u = __shfl_sync(0xffffffffu, T, 0);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint64_t dQ[2] = {umma_desc_sw64(smem_u32(smem + FwdSmem::q)), umma_desc_sw64(smem_u32(smem + FwdSmem::q + 8192))};
+      const uint64_t dQ[2] = {umma_desc_sw64(smem_u32(smem + FwdSmem::q + (item_n & 1) * 16384)),
+                              umma_desc_sw64(smem_u32(smem + FwdSmem::q + (item_n & 1) * 16384 + 8192))};
       const uint32_t stream = smem_u32(smem + FwdSmem::stream);
-      mbar_wait(q_full, 0);
+      mbar_wait(&q_full[item_n & 1], (item_n >> 1) & 1);
       tc_fence_after();
       for (int j = 0; j < T_u; ++j) {
-        const int stage = j % kNST;
-        mbar_wait(&st_full[stage], (j / kNST) & 1);
+        const int gj = base + j;                     // key-tile counter across items
+        const int stage = gj % kNST;
+        mbar_wait(&st_full[stage], (gj / kNST) & 1);
         const uint64_t dK = umma_desc_sw64(stream + stage * 16384);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(&s_free[g], (j & 1) ^ 1);
+          mbar_wait(&s_free[g], (gj & 1) ^ 1);
           tc_fence_after();
           if (elect_one()) {
             umma_bf16(tmem_u + g * 128, dQ[g], dK, idesc, 0u);
@@ -843,13 +898,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t stream = smem_u32(smem + FwdSmem::stream);
       for (int j = 0; j < T_u; ++j) {
-        const int stage = j % kNST;
+        const int gj = base + j;
+        const int stage = gj % kNST;
         // V tile [128 keys][32 dims] (64-byte rows, SWIZZLE_64B) read MN-major: N = dims contiguous, K = keys, a K step of
         // 16 keys = 1024 B -- no transposed copy of V exists
         const uint64_t dV = umma_desc_sw64(stream + stage * 16384 + 8192);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_ready[g], j & 1);
+          mbar_wait(&p_ready[g], gj & 1);
           tc_fence_after();
           const uint32_t pa = tmem_u + 256 + g * 64, oa = tmem_u + 384 + g * 32;
           if (elect_one()) {
@@ -886,12 +942,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     };
     prefetch(0);
     for (int j = 0; j < T; ++j) {
+      const int gj = base + j;                       // key-tile counter across items (barrier parities)
       const bool need_mask = (tile_list[j] & (g == 0 ? 0x4000 : 0x8000)) != 0;
-      int* s_id = ids_base + (j & 1) * 128;
+      int* s_id = ids_base + (gj & 1) * 128;
       s_id[tid] = pre_i;
       named_bar_sync(1 + g, 128);
       prefetch(j + 1);
-      mbar_wait(&s_full[g], j & 1);
+      mbar_wait(&s_full[g], gj & 1);
       tc_fence_after();
       uint32_t sv[2][32];
       auto mask_chunk = [&](uint32_t (&v)[32], int c) {
@@ -945,7 +1002,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
           if (c == 0 && optimistic) {
             // P_g is reusable and O_g quiescent once the previous tile's P V MMAs have retired
-            mbar_wait(&p_free[g], (j & 1) ^ 1);
+            mbar_wait(&p_free[g], (gj & 1) ^ 1);
             tc_fence_after();
             apply_pending();
           }
@@ -984,7 +1041,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
         const float alpha = (raise && m_run != -INFINITY) ? fast_ex2(m_run - m_use) : 1.f;
         if (two_pass) {                                  // (a redone optimistic sweep already waited for p_free)
-          mbar_wait(&p_free[g], (j & 1) ^ 1);
+          mbar_wait(&p_free[g], (gj & 1) ^ 1);
           tc_fence_after();
           apply_pending();
         }
@@ -1004,7 +1061,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
     // ---- epilogue: O / l -> bf16, LSE ----
     if (T > 0) {
-      mbar_wait(&p_free[g], (T & 1) ^ 1);              // the last P V MMAs have retired
+      mbar_wait(&p_free[g], ((base + T) & 1) ^ 1);     // the last P V MMAs have retired
       tc_fence_after();
     }
     uint32_t ov[32];
@@ -1031,11 +1088,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   }
 
+  // ---- end of the item: every role has drained (O read out, all MMAs retired, tile list no longer needed) ----
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  base += T;
+  }   // item loop
+
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) {
+    // the last CTA out re-arms the hand-out for the next launch
+    if (atomicAdd(&g_fwd_items[1], 1u) == gridDim.x - 1) {
+      g_fwd_items[0] = 0u;
+      g_fwd_items[1] = 0u;
+      __threadfence();
+    }
   }
 }
 
@@ -1198,7 +1270,10 @@ FK_API int fk_attn_forward_tc(const void* q, const void* k, const void* v, void*
   p.qid = qid; p.kid = kid; p.qmin = qmin; p.qmax = qmax; p.kmin = kmin; p.kmax = kmax;
   p.out = static_cast<__nv_bfloat16*>(out); p.lse = lse; p.o_bs = o_bs; p.o_ts = o_ts;
   p.B = B; p.H = H; p.Sq = S; p.Sk = S; p.scale_log2 = scale * 1.4426950408889634f;
-  attn_fwd_tc_kernel<<<dim3((S + 255) / 256, H, B), kFwdThreads, FwdSmem::total, stream>>>(mQ, mK, mV, p);
+  // persistent CTAs: one per SM (or per work item when there are fewer), looping over (256-query block, head, trial) items
+  const long long n_items = static_cast<long long>((S + 255) / 256) * H * B;
+  FK_REQUIRE(n_items < (1ll << 31), "fk_attn_forward_tc: too many work items");
+  attn_fwd_tc_kernel<<<static_cast<unsigned>(n_items < bwd_sm_count() ? n_items : bwd_sm_count()), kFwdThreads, FwdSmem::total, stream>>>(mQ, mK, mV, p);
   FK_CHECK_LAUNCH();
   fk_count_launch();
   return FK_OK;
