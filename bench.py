@@ -38,8 +38,8 @@ CPU_SAMPLE_TRIALS = 2
 # (attention rows: the capture in profiles/r01_attention_tc_ncu_full.txt is a 16-trial launch; trials are independent,
 #  so a B-trial launch moves B/16 times those bytes)
 NCU_TRAFFIC = {"vq_search": 12660224}
-NCU_TRAFFIC_PER_16_TRIALS = {"attn_fwd": 201729792 + 55561984, "attn_bwd_dkv": 277267200 + 111549184,
-                             "attn_bwd_dq": 277148928 + 56863744}
+NCU_TRAFFIC_PER_16_TRIALS = {"attn_fwd": 202000896 + 54899712, "attn_bwd_dkv": 277223424 + 112426240,
+                             "attn_bwd_dq": 277200640 + 58217984}
 
 
 def model_configs():
