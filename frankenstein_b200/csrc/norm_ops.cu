@@ -191,6 +191,23 @@ norm_bwd_kernel(const TIn* __restrict__ x, const TG* __restrict__ g, const float
 // ------------------------------------------------------------------------------------------------
 // SwiGLU gate on the fused [M, 2H] projection (columns [0,H) = w1 x, [H,2H) = w3 x), bf16.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 swiglu8(const uint4 a, const uint4 b) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t ow[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]), bv = *reinterpret_cast<const __nv_bfloat162*>(&bw[j]);
+    const float a0 = __bfloat162float(av.x), a1 = __bfloat162float(av.y);
+    // silu is rounded to bf16 before the product, as the reference's two separate bf16 ops do
+    // (__fdividef: 2-ulp division, one MUFU.RCP instead of the IEEE division sequence; the result is rounded to bf16)
+    const float s0 = __bfloat162float(__float2bfloat16_rn(__fdividef(a0, 1.f + __expf(-a0))));
+    const float s1 = __bfloat162float(__float2bfloat16_rn(__fdividef(a1, 1.f + __expf(-a1))));
+    __nv_bfloat162 o = __floats2bfloat162_rn(s0 * __bfloat162float(bv.x), s1 * __bfloat162float(bv.y));
+    ow[j] = *reinterpret_cast<uint32_t*>(&o);
+  }
+  return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
 __global__ void __launch_bounds__(256)
 swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ h13, __nv_bfloat16* __restrict__ y, long long M, int H) {
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
@@ -199,19 +216,7 @@ swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ h13, __nv_bfloat16* __restri
   const int c = static_cast<int>(idx % H);
   const uint4 a = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + c);
   const uint4 b = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + H + c);
-  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-  uint32_t ow[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]), bv = *reinterpret_cast<const __nv_bfloat162*>(&bw[j]);
-    const float a0 = __bfloat162float(av.x), a1 = __bfloat162float(av.y);
-    // silu is rounded to bf16 before the product, as the reference's two separate bf16 ops do
-    const float s0 = __bfloat162float(__float2bfloat16_rn(a0 / (1.f + __expf(-a0))));
-    const float s1 = __bfloat162float(__float2bfloat16_rn(a1 / (1.f + __expf(-a1))));
-    __nv_bfloat162 o = __floats2bfloat162_rn(s0 * __bfloat162float(bv.x), s1 * __bfloat162float(bv.y));
-    ow[j] = *reinterpret_cast<uint32_t*>(&o);
-  }
-  *reinterpret_cast<uint4*>(y + idx) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  *reinterpret_cast<uint4*>(y + idx) = swiglu8(a, b);
 }
 
 __global__ void __launch_bounds__(256)
@@ -235,7 +240,7 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ h13, const __nv_bfloat16* __
     const float gg[2] = {__bfloat162float(gv.x), __bfloat162float(gv.y)};
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float sig = 1.f / (1.f + __expf(-aa[e]));
+      const float sig = __fdividef(1.f, 1.f + __expf(-aa[e]));
       const float silu = aa[e] * sig;
       ra[e] = gg[e] * bb[e] * sig * (1.f + aa[e] * (1.f - sig));
       rb[e] = gg[e] * silu;
