@@ -34,6 +34,9 @@ TRIALS_PER_GPU = 128
 T_BINS, N_CH = 512, 512
 VQ_K, VQ_D, VQ_C = 8192, 256, 256
 CPU_SAMPLE_TRIALS = 2
+WORKLOAD = ("cfg4-joint: SoundStream(C=256,D=256,K=8192,euclid) on 512 ch + BrainFormer(Encoder window 512, "
+            "256 electrodes, patch 32 -> 4096 tokens/trial, dim 512, 4 layers, 16x32 heads, hidden 2048; "
+            "perceiver 32 tokens) on 256 ch; AdamW + value clip")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 # (attention rows: the capture in profiles/r01_attention_tc_ncu_full.txt is a 16-trial launch; trials are independent,
 #  so a B-trial launch moves B/16 times those bytes)
@@ -182,8 +185,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "trials/sec VQ+Brainformer train step", "value": base["value"], "unit": "trials/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg4-joint (SoundStream K=8192 D=256 + BrainFormer 4096 tokens/trial dim 512), CPU sample",
-                       "trials_per_step": CPU_SAMPLE_TRIALS},
+            "config": {"workload": WORKLOAD, "trials_per_gpu": TRIALS_PER_GPU, "bins": T_BINS,
+                       "sample": f"bounded CPU sample of the same step: {CPU_SAMPLE_TRIALS} trials per timed step, scaled to trials/s"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -344,10 +347,7 @@ def main():
             "metric": "trials/sec VQ+Brainformer train step", "value": total_trials / (ms_total * 1e-3), "unit": "trials/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "cfg4-joint: SoundStream(C=256,D=256,K=8192,euclid) on 512 ch + BrainFormer(Encoder window 512, "
-                                   "256 electrodes, patch 32 -> 4096 tokens/trial, dim 512, 4 layers, 16x32 heads, hidden 2048; "
-                                   "perceiver 32 tokens) on 256 ch; AdamW + value clip",
-                       "trials_per_gpu": B, "global_batch": B * world, "bins": T_BINS, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD, "trials_per_gpu": B, "global_batch": B * world, "bins": T_BINS, "parallelism": f"dp{world}",
                        "l2_policy": "inputs larger than L2 (134 MB batch rotated over a 3-batch pool)"},
             "clocks": clk,
             "e2e": {"value": total_trials / (ms_e2e * 1e-3), "unit": "trials/s", "h2d_bytes_per_step": h2d_bytes,
