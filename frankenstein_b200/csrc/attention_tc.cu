@@ -277,6 +277,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   unsigned long long g_start = 0;
   if (kProf == 2 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
   long long* prof = kProf ? p.prof + static_cast<long long>(item) * 24 : nullptr;
+  // per-tile event stamps of the first item of CTA 0 (kFull only): trace[event][tile], after the counters
+  long long* trace = (kFull && blockIdx.x == 0 && item_n == 0) ? p.prof + static_cast<long long>(n_items) * 24 : nullptr;
   const uint16_t* tile_list = tile_lists + (item_n & 1) * kMaxTiles;     // made visible by the previous item's final barrier
   const int T = n_tiles_slot[item_n & 1];
   if (kFull && threadIdx.x == 0) { prof[1] = clock64() - t_start; prof[2] = T; }
@@ -364,6 +366,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         const int stage = gt % kNST, g = gt % kNG, n = gt / kNG;
         wait_acc<kProf>(&st_full[stage], (gt / kNST) & 1, w_sf);
         wait_acc<kProf>(&stage_free[g], (n & 1) ^ 1, w_free);
+        if (kFull && trace && lane == 0 && js < 128) trace[2 * 128 + js] = clock64();
         tc_fence_after();
         const uint64_t dS = umma_desc_sw64(stream + stage * 16384), dD = umma_desc_sw64(stream + stage * 16384 + 4096);
         if (elect_one()) {
@@ -375,6 +378,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
           umma_commit(&sdp_full[g]);
         }
         __syncwarp();
+        if (kFull && trace && lane == 0 && js < 128) trace[3 * 128 + js] = clock64();
       }
       if (kFull && lane == 0) { prof[11] = w_sf; prof[12] = w_free; }
     }
@@ -390,6 +394,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         const int gt = base + ia;                    // tile counter across items
         const int stage = gt % kNST, g = gt % kNG, n = gt / kNG;
         wait_acc<kProf>(&p_ready[g], n & 1, w_pr);
+        if (kFull && trace && lane == 0 && ia < 128) trace[0 * 128 + ia] = clock64();
         tc_fence_after();
         const uint32_t ta = tmem_u + g * 128;             // P pairs at +0..31, dS pairs at +64..95 (written in place)
         if (p.mn_major) {
@@ -419,6 +424,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
           }
         }
         __syncwarp();
+        if (kFull && trace && lane == 0 && ia < 128) trace[1 * 128 + ia] = clock64();
       }
       if (elect_one()) umma_commit(acc_full);
       __syncwarp();
@@ -484,6 +490,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       prefetch(j + kNG);
       wait_acc<kProf>(&sdp_full[g], n & 1, w_full);
       if (prof_me && j == j0) prof[3] = clock64() - t_start;
+      if (kFull && trace && q4 == 0 && lane == 0 && j < 128) trace[4 * 128 + j] = clock64();
       const long long tc0 = kFull ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + g * 128;
@@ -562,6 +569,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[g]);
+      if (kFull && trace && q4 == 0 && lane == 0 && j < 128) trace[5 * 128 + j] = clock64();
       if (kFull) w_comp += clock64() - tc0;
     }
     if (prof_me) { prof[4] = w_full; prof[6] = w_bar; prof[7] = w_comp; prof[8] = clock64() - t_start; }

@@ -21,7 +21,7 @@ def main():
     w = torch.randn(B, S, H * 32, device=dev, dtype=torch.bfloat16)
     n_cta = B * H * (S // 128)
     for parts, name in ((2, "dK/dV kernel"), (4, "dQ kernel")):
-        prof = torch.zeros(n_cta, 24, device=dev, dtype=torch.int64)
+        prof = torch.zeros(n_cta * 24 + 6 * 128, device=dev, dtype=torch.int64)
         check(lib().fk_attn_set_profile_buffer(ptr(prof), 1), "set")
         ops._BWD_PARTS = (parts,)
         for _ in range(2):
@@ -31,13 +31,31 @@ def main():
         ops._BWD_PARTS = (2, 4)
         torch.cuda.synchronize()
         check(lib().fk_attn_set_profile_buffer(None, 1), "unset")
-        p = prof.double().cpu()
+        tr = prof[n_cta * 24:].cpu().view(6, 128)
+        p = prof[:n_cta * 24].view(n_cta, 24).double().cpu()
         p = p[p[:, 2] > 0]
         life = p[:, 0].mean().item()
         T = p[:, 2].mean().item()
         print(f"{name}: {p.shape[0]} CTAs, mean tiles {T:.1f}, mean lifetime {life:.0f} cycles = {life / T:.0f} per tile")
         for i, n in enumerate(NAMES):
             print(f"  {n:26s} mean {p[:, i].mean().item():9.0f}  ({100 * p[:, i].mean().item() / life:5.1f} % of lifetime)")
+        # per-tile event trace of the first item of CTA 0: 0 acc issuer saw p_ready, 1 acc MMAs issued, 2 score issuer saw
+        # stage_free, 3 score MMAs issued, 4 warpgroup saw sdp_full, 5 warpgroup arrived on p_ready
+        nt = int((tr[5] > 0).sum().item())
+        if nt > 12 and bool((tr[:, :nt] > 0).all()):
+            sl = slice(6, nt - 3)
+            a0, a1, s2, s3, w4, w5 = [tr[i].double() for i in range(6)]
+            hop1 = (a0[sl] - w5[sl]).mean().item()                       # p_ready arrive -> acc issuer awake
+            iss1 = (a1[sl] - a0[sl]).mean().item()                       # acc issue
+            j3 = slice(9, nt)                                            # tile j+3 reuses the stage of tile j
+            j0_ = slice(6, nt - 3)
+            hop2 = (s2[j3] - a1[j0_]).mean().item()                     # acc MMAs exec + stage_free -> score issuer awake
+            iss2 = (s3[j3] - s2[j3]).mean().item()
+            hop3 = (w4[j3] - s3[j3]).mean().item()                       # score MMAs exec + sdp_full -> warpgroup awake
+            comp = (w5[sl] - w4[sl]).mean().item()
+            print(f"  stage turnaround trace (tiles 6..{nt - 4}): p_ready->acc issuer {hop1:.0f}, acc issue {iss1:.0f}, "
+                  f"acc exec + stage_free->score issuer {hop2:.0f}, score issue {iss2:.0f}, score exec + sdp_full->warpgroup {hop3:.0f}, "
+                  f"compute (sdp_full seen -> p_ready) {comp:.0f} cycles")
         steady = (p[:, 8] - p[:, 3]).mean().item()
         print(f"  steady state (first scores -> last P ready): {steady:.0f} cycles = {steady / T:.0f} per tile; "
               f"prologue {p[:, 3].mean().item():.0f}, tail {(p[:, 0] - p[:, 8]).mean().item():.0f}")
