@@ -364,18 +364,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       for (int js = 0; js < T_u; ++js) {
         const int gt = base + js;                    // tile counter across items
         const int stage = gt % kNST, g = gt % kNG, n = gt / kNG;
+        // (operands of the MMAs are formed BEFORE the waits: ~50 uniform-datapath instructions that would otherwise sit
+        //  on the critical path stage_free -> score MMAs)
+        uint64_t dS = umma_desc_sw64(stream + stage * 16384), dD = umma_desc_sw64(stream + stage * 16384 + 4096);
+        uint32_t d_s = tmem_u + g * 128, d_dp = tmem_u + g * 128 + 64;
+        uint64_t* const bar_full = &sdp_full[g];
+        {
+          // pin the values here: without this the compiler sinks the whole address arithmetic below the waits again
+          asm volatile("" : "+l"(dS), "+l"(dD), "+r"(d_s), "+r"(d_dp));
+        }
         wait_acc<kProf>(&st_full[stage], (gt / kNST) & 1, w_sf);
         wait_acc<kProf>(&stage_free[g], (n & 1) ^ 1, w_free);
         if (kFull && trace && lane == 0 && js < 128) trace[2 * 128 + js] = clock64();
         tc_fence_after();
-        const uint64_t dS = umma_desc_sw64(stream + stage * 16384), dD = umma_desc_sw64(stream + stage * 16384 + 4096);
         if (elect_one()) {
           // a K step of 16 bf16 = 32 bytes = +2 in the descriptor's (address >> 4) field
-          umma_bf16(tmem_u + g * 128, dA, dS, idesc_score, 0u);
-          umma_bf16(tmem_u + g * 128, dA + 2, dS + 2, idesc_score, 1u);
-          umma_bf16(tmem_u + g * 128 + 64, dB, dD, idesc_score, 0u);
-          umma_bf16(tmem_u + g * 128 + 64, dB + 2, dD + 2, idesc_score, 1u);
-          umma_commit(&sdp_full[g]);
+          umma_bf16(d_s, dA, dS, idesc_score, 0u);
+          umma_bf16(d_s, dA + 2, dS + 2, idesc_score, 1u);
+          umma_bf16(d_dp, dB, dD, idesc_score, 0u);
+          umma_bf16(d_dp, dB + 2, dD + 2, idesc_score, 1u);
+          umma_commit(bar_full);
         }
         __syncwarp();
         if (kFull && trace && lane == 0 && js < 128) trace[3 * 128 + js] = clock64();
@@ -393,23 +401,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       for (int ia = 0; ia < T_u; ++ia) {
         const int gt = base + ia;                    // tile counter across items
         const int stage = gt % kNST, g = gt % kNG, n = gt / kNG;
+        // (operands formed before the wait, see the score issuer)
+        uint32_t ta = tmem_u + g * 128;                   // P pairs at +0..31, dS pairs at +64..95 (written in place)
+        uint64_t dMA = umma_desc_sw64(stream + stage * 16384 + 4096), dMB = umma_desc_sw64(stream + stage * 16384);
+        uint64_t* const bar_free = &stage_free[g];
+        uint64_t* const bar_empty = &st_empty[stage];
+        asm volatile("" : "+l"(dMA), "+l"(dMB), "+r"(ta));      // pin (see the score issuer)
         wait_acc<kProf>(&p_ready[g], n & 1, w_pr);
         if (kFull && trace && lane == 0 && ia < 128) trace[0 * 128 + ia] = clock64();
         tc_fence_after();
-        const uint32_t ta = tmem_u + g * 128;             // P pairs at +0..31, dS pairs at +64..95 (written in place)
         if (p.mn_major) {
           // B operand straight from the score stage: tile [64 tokens][32 dims], 64-byte rows, SWIZZLE_64B = the canonical
           // MN-major layout (N = 32 dims contiguous, 8-token groups 512 B apart); a K step of 16 tokens = 1024 B.
           // DKV: dV += P^T dO (stB), dK += dS^T Q (stA).  DQ: dQ += dS K (stA).
-          const uint64_t dMA = umma_desc_sw64(stream + stage * 16384 + 4096), dMB = umma_desc_sw64(stream + stage * 16384);
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               if (MODE == MODE_DKV) umma_bf16_ts(tmem_u + kAccCol, ta + kk * 8, dMA + 64 * kk, idesc_acc | (1u << 16), (ia > 0 || kk > 0) ? 1u : 0u);
               umma_bf16_ts(tmem_u + kAccCol + 32, ta + 64 + kk * 8, dMB + 64 * kk, idesc_acc | (1u << 16), (ia > 0 || kk > 0) ? 1u : 0u);
             }
-            umma_commit(&stage_free[g]);
-            umma_commit(&st_empty[stage]);
+            umma_commit(bar_free);
+            umma_commit(bar_empty);
           }
         } else {
           const uint64_t dTA = umma_desc_sw128(stream + stage * 16384 + 8192), dTB = umma_desc_sw128(stream + stage * 16384 + 12288);
