@@ -86,6 +86,54 @@ def test_attention_forward_running_max_paths(growth):
     close(out.reshape(B, S, H, 32), ref, what=f"running-max path, growth {growth}")
 
 
+def test_attention_full_size_properties():
+    """Full cfg-2 sequence (S = 4096 tokens, 16 heads, block-causal with 256 electrodes), where the dense oracle is too
+    large to run in a test: size-independent properties instead.  (1) block causality is exact: changing keys / values of
+    time step >= t leaves the outputs AND the input gradients of all earlier time steps bit-identical, and a loss on the
+    earlier time steps sends exactly zero gradient to later tokens; (2) linearity in V; (3) a spot check of 64 random rows against fp32 softmax attention computed row by row."""
+    from frankenstein_b200 import ops
+    B, S, H, E = 2, 4096, 16, 256
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(11)
+    qkv = (torch.randn(B, S, 3 * H * 32, generator=g) * 1.2).to(dev).to(torch.bfloat16)
+    mask = ops.LabelMask.block_causal(B, S, E, dev)
+
+    def run(x, w=None):
+        xx = x.clone().requires_grad_(True)
+        out = ops.attention_qkv(xx * 1.0, H, None, mask)
+        if w is None:
+            return out.detach(), None
+        (out.float() * w).sum().backward()
+        return out.detach(), xx.grad.detach()
+
+    w = torch.randn(B, S, H * 32, generator=g).to(dev)
+    t0 = 9 * E                                            # boundary between time steps 8 and 9
+    w_early = w.clone(); w_early[:, t0:] = 0              # loss that only looks at the earlier time steps
+    out_a, grad_a = run(qkv, w_early)
+    pert = qkv.clone()
+    pert[:, t0:, H * 32:] = (torch.randn(B, S - t0, 2 * H * 32, generator=g) * 1.2).to(dev).to(torch.bfloat16)   # later k and v
+    out_b, grad_b = run(pert, w_early)
+    assert torch.equal(out_a[:, :t0], out_b[:, :t0]), "outputs of earlier time steps changed with later keys/values"
+    assert torch.equal(grad_a[:, :t0], grad_b[:, :t0]), "gradients of earlier tokens changed with later keys/values"
+    assert grad_a[:, t0:].abs().max().item() == 0.0, "later tokens received gradient from a loss on earlier time steps"
+    # linearity in V
+    v2 = qkv.clone(); v2[..., 2 * H * 32:] = (torch.randn(B, S, H * 32, generator=g)).to(dev).to(torch.bfloat16)
+    vs = qkv.clone(); vs[..., 2 * H * 32:] = (qkv[..., 2 * H * 32:].float() + v2[..., 2 * H * 32:].float()).to(torch.bfloat16)
+    o1, _ = run(qkv); o2, _ = run(v2); o3, _ = run(vs)
+    close(o3, o1.float() + o2.float(), rtol=2e-2, what="linearity in V")
+    # spot check of random rows against fp32 softmax
+    q, k, v = qkv.float().view(B, S, 3, H, 32).unbind(2)
+    rows = torch.randint(0, S, (64,), generator=g).tolist()
+    for i in rows[:64]:
+        b, hh = i % B, i % H
+        vis = (torch.arange(S, device=dev) // E) <= (i // E)
+        sc = (k[b, :, hh] @ q[b, i, hh]) / math.sqrt(32.0)
+        p_ = torch.softmax(sc.masked_fill(~vis, float("-inf")), dim=0)
+        ref = p_ @ v[b, :, hh]
+        got = o1[b, i].view(H, 32)[hh].float()
+        assert (got - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 2e-3, f"row {i}"
+
+
 @pytest.mark.parametrize("per_sample", [False, True])
 def test_rope_matches_reference_formula(per_sample):
     from frankenstein_b200 import ops
