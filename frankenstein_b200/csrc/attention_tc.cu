@@ -46,6 +46,9 @@ struct TcParams {
   long long o0_bs, o0_ts, o1_bs, o1_ts;
   int B, H, S_row, S_col, Sq;
   float scale, scale_log2;
+  const float2* rope_table;                            // [rope_len][16] (cos, sin) or null: inverse RoPE fused into the
+  const int* rope_pos;                                 // store of dK / dQ (position of row = rope_pos ? rope_pos[b][row]
+  int rope_len, rope_offset;                           //  : row + rope_offset), replacing two fk_rope passes per layer
   long long* prof;                                     // kProf instantiation: [n_ctas][16] cycle counters
   int mn_major;                                        // 1: the accumulate MMAs read their B operand (Q / dO / K tile,
                                                        // [64 tokens][32 dims]) MN-major from the score stage itself;
@@ -604,12 +607,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         const float sc = (which == 1) ? p.scale : 1.f;
         __nv_bfloat16* dst = (which == 0 ? p.out0 + b * p.o0_bs + static_cast<long long>(row) * p.o0_ts
                                          : p.out1 + b * p.o1_bs + static_cast<long long>(row) * p.o1_ts) + h * 32;
+        // gradient of a rotated operand (dK / dQ): rotate back (conjugate), as fk_rope(inverse = 1) would afterwards
+        const float2* tb = nullptr;
+        if (which == 1 && p.rope_table != nullptr) {
+          int ps = p.rope_pos ? p.rope_pos[static_cast<long long>(b) * p.S_row + row] : row + p.rope_offset;
+          ps = min(max(ps, 0), p.rope_len - 1);
+          tb = p.rope_table + static_cast<long long>(ps) * 16;
+        }
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            w[e] = pack2(__uint_as_float(acc[c4 * 8 + e * 2]) * sc, __uint_as_float(acc[c4 * 8 + e * 2 + 1]) * sc);
+          for (int e = 0; e < 4; ++e) {
+            float a0 = __uint_as_float(acc[c4 * 8 + e * 2]) * sc, a1 = __uint_as_float(acc[c4 * 8 + e * 2 + 1]) * sc;
+            if (tb != nullptr) {
+              const float2 cs = tb[c4 * 4 + e];
+              const float r0 = a0 * cs.x + a1 * cs.y, r1 = a1 * cs.x - a0 * cs.y;
+              a0 = r0; a1 = r1;
+            }
+            w[e] = pack2(a0, a1);
+          }
           *reinterpret_cast<uint4*>(dst + c4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
@@ -1174,9 +1191,11 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
                                long long k_ts, long long v_bs, long long v_ts, long long do_bs, long long do_ts,
                                long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
                                long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
-                               const int* kmin, const int* kmax, float scale, int parts, void* stream_) {
+                               const int* kmin, const int* kmax, float scale, const float* rope_table, int rope_len,
+                               const int* rope_pos, int rope_offset, int parts, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(head_dim == 32, "fk_attn_backward_tc: only head_dim 32 is built");
+  FK_REQUIRE(rope_table == nullptr || rope_len > 0, "fk_attn_backward_tc: rope_len must be positive with a rope table");
   FK_REQUIRE(q && k && v && d_o && lse && delta && B > 0 && H > 0 && S > 0, "fk_attn_backward_tc: bad argument");
   FK_REQUIRE((parts & ~6) == 0 && parts != 0, "fk_attn_backward_tc: parts is a bitmask of 2 (dK/dV) and 4 (dQ)");
   FK_REQUIRE((qid == nullptr) == (kid == nullptr), "fk_attn_backward_tc: qid and kid go together");
@@ -1236,6 +1255,7 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = g_attn_prof;
     p.mn_major = mn_major;
+    p.rope_table = reinterpret_cast<const float2*>(rope_table); p.rope_pos = rope_pos; p.rope_len = rope_len; p.rope_offset = rope_offset;
     if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DKV, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
     else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DKV, 1><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
     else attn_bwd_tc_kernel<MODE_DKV, 0><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
@@ -1250,6 +1270,7 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = g_attn_prof;
     p.mn_major = mn_major;
+    p.rope_table = reinterpret_cast<const float2*>(rope_table); p.rope_pos = rope_pos; p.rope_len = rope_len; p.rope_offset = rope_offset;
     if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DQ, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
     else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DQ, 1><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
     else attn_bwd_tc_kernel<MODE_DQ, 0><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);

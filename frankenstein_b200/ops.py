@@ -320,6 +320,9 @@ class _AttnQKVFn(torch.autograd.Function):
                                              *common, part, stream()), "fk_attn_backward")
 
         legacy("attn_delta", 1)
+        rope_done = False
+        r = ctx.rope
+        rope_args = (ptr(r.table), r.table.shape[0], ptr(r.pos), r.offset) if r is not None else (0, 0, 0, 0)
         if ATTN_BWD_IMPL == "legacy":
             legacy("attn_bwd_dkv", 2)
             legacy("attn_bwd_dq", 4)
@@ -345,9 +348,10 @@ class _AttnQKVFn(torch.autograd.Function):
                                                     ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv), B, H, S, hd,
                                                     q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                                                     d4.stride(0), d4.stride(1), dq.stride(0), dq.stride(1), dk.stride(0),
-                                                    dk.stride(1), dv.stride(0), dv.stride(1), *common, part, stream()),
+                                                    dk.stride(1), dv.stride(0), dv.stride(1), *common, *rope_args, part, stream()),
                           "fk_attn_backward_tc")
-        if ctx.rope is not None:
+            rope_done = True                          # dq / dk were rotated back inside the kernels
+        if ctx.rope is not None and not rope_done:
             _rope_inplace(dq, ctx.rope, True)
             _rope_inplace(dk, ctx.rope, True)
         return dqkv, None, None, None, None

@@ -158,7 +158,10 @@ int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void*
                         long long k_ts, long long v_bs, long long v_ts, long long do_bs, long long do_ts,
                         long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
                         long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
-                        const int* kmin, const int* kmax, float scale, int parts, void* stream);
+                        const int* kmin, const int* kmax, float scale,
+                        const float* rope_table /* [rope_len][16][2] (cos, sin) or NULL: dq / dk are rotated back (the gradient of
+                                                   apply_rope, brainformer.py:70-91) inside the kernel */,
+                        int rope_len, const int* rope_pos /* [B][S] or NULL */, int rope_offset, int parts, void* stream);
 
 /* tcgen05 / TMEM / TMA forward (attention_tc.cu): q / k / v are strided views ([B][S][H][32], strides in elements);
  * the V tile is read MN-major by the P V MMAs, so no transposed copy is needed; Sq == Sk == S. */
