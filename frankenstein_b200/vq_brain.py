@@ -10,8 +10,9 @@ underneath:
 * ``custom_l1_loss`` is one fused masked-sum kernel (no ``nonzero`` host sync, no dynamic shape);
 * ``calculate_perp`` is computed from the code histogram (no ``[N, K]`` one-hot).
 
-The causal conv / transposed-conv stacks are cuDNN library convolutions exactly as in the
-reference (SURVEY.md section 8f row N1 lists them as the next kernel to write).
+The causal conv / transposed-conv stacks are cuDNN library convolutions as in the reference
+(SURVEY.md section 8f row N1 lists them as the next kernel to write), run channels-last so that no
+permute copies or layout-conversion kernels surround them.
 """
 from __future__ import annotations
 
@@ -31,6 +32,11 @@ class CausalConv1d(nn.Conv1d):
         self.causal_padding = self.dilation[0] * (self.kernel_size[0] - 1)
 
     def forward(self, x):
+        if x.dim() == 4:
+            # channels-last path ([B, C, 1, T] with NHWC strides, see _ChannelsFirstStack): the same convolution as a
+            # 1 x k conv2d, so that cuDNN runs its NHWC kernels without a layout conversion before and after
+            return F.conv2d(F.pad(x, [self.causal_padding, 0]), self.weight.unsqueeze(2), self.bias,
+                            stride=(1, self.stride[0]), dilation=(1, self.dilation[0]), groups=self.groups)
         return self._conv_forward(F.pad(x, [self.causal_padding, 0]), self.weight, self.bias)
 
 
@@ -45,11 +51,26 @@ class CausalConvTranspose1d(nn.ConvTranspose1d):
     def forward(self, x, output_size=None):
         if self.padding_mode != 'zeros':
             raise ValueError('Only `zeros` padding mode is supported for ConvTranspose1d')
+        if x.dim() == 4:                                    # channels-last path (see CausalConv1d)
+            y = F.conv_transpose2d(x, self.weight.unsqueeze(2), self.bias, stride=(1, self.stride[0]),
+                                   padding=(0, self.padding[0]), output_padding=(0, self.output_padding[0]),
+                                   groups=self.groups, dilation=(1, self.dilation[0]))
+            return y[..., :-self.causal_padding]
         output_padding = self._output_padding(x, output_size, self.stride, self.padding, self.kernel_size,
                                               self.dilation)
         y = F.conv_transpose1d(x, self.weight, self.bias, self.stride, self.padding, output_padding, self.groups,
                                self.dilation)
         return y[..., :-self.causal_padding]
+
+
+class _PointwiseConv1d(nn.Conv1d):
+    """nn.Conv1d (same parameters / state-dict keys) that also takes the channels-last 4-D layout."""
+
+    def forward(self, x):
+        if x.dim() == 4:
+            return F.conv2d(x, self.weight.unsqueeze(2), self.bias, stride=(1, self.stride[0]),
+                            padding=(0, self.padding[0]), dilation=(1, self.dilation[0]), groups=self.groups)
+        return super().forward(x)
 
 
 def _interleave_elu(mods):
@@ -70,7 +91,7 @@ class ResidualUnit(nn.Module):
         self.dilation = dilation
         self.layers = _interleave_elu([
             CausalConv1d(in_channels, out_channels, kernel_size=3, dilation=dilation),
-            nn.Conv1d(out_channels, in_channels, kernel_size=1),
+            _PointwiseConv1d(out_channels, in_channels, kernel_size=1),
         ])
 
     def forward(self, x):
@@ -107,9 +128,15 @@ class DecoderBlock(nn.Module):
 
 
 class _ChannelsFirstStack(nn.Module):
-    """[B, T, C] in and out; the conv stack itself runs channels-first like the reference."""
+    """[B, T, C] in and out.  The reference permutes to [B, C, T] (vq_brain.py:135-137, 156-158) and cuDNN then converts
+    to NHWC and back around every convolution.  Here [B, T, C] is viewed, without a copy, as the channels-last 4-D tensor
+    [B, C, 1, T] (its NHWC strides are exactly those of a contiguous [B, T, C]), every layer is the equivalent 1 x k
+    conv2d, and the result is viewed back: no permute copies and no layout-conversion kernels."""
 
     def forward(self, x):
+        if x.is_cuda and x.dim() == 3 and x.is_contiguous():
+            y = self.layers(x.transpose(1, 2).unsqueeze(2))          # [B, C, 1, T], channels_last strides
+            return y.squeeze(2).transpose(1, 2)
         return self.layers(x.transpose(1, 2)).transpose(1, 2)
 
 
