@@ -351,9 +351,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
     }
   } else if (warp == 1) {
     // ================================ score-MMA issuer ================================
-    // (measured on B200: one thread sustains one tcgen05.mma per ~97 cycles and the tensor core accepts one per
-    //  ~60 cycles whatever N <= 128 is -- scripts/microbench/umma_rate.cu -- so the score MMAs and the accumulate
-    //  MMAs are issued by two different threads.)
+    // (the score MMAs and the accumulate MMAs are issued by two different warps so that neither waits behind the other's
+    //  barrier; issuing both from one thread, back to back without a barrier between the reader and the overwriter of
+    //  a stage, was measured 13 % slower -- DESIGN.md section 4.2)
     {
       constexpr uint32_t idesc_score = umma_idesc_bf16(kRows, kCols);
       const int T_u = __shfl_sync(0xffffffffu, T, 0);
@@ -702,12 +702,13 @@ attn_transpose_kernel(const __nv_bfloat16* __restrict__ x, long long bs, long lo
 }
 
 // ================================================================================================
-// Forward on tcgen05: CTA = 256 queries (two warpgroups, 128 rows each, one thread per row), streams 128-key
-// tiles (K as [keys][32] SW64, V as the transposed copy Vt [32][keys] SW128).  Per tile and warpgroup g:
-//   S_g = Q_g K^T (2 MMAs, N = 128) -> TMEM;  thread: pass 1 row max, pass 2 P = 2^(S c - m), row sum, bf16 pairs
-//   -> operand buffer in TMEM;  O_g += P V (8 TS-mode MMAs, N = 32) accumulating in TMEM.
-// Online softmax with LAZY rescaling: the running max m is only raised (and O, l rescaled) when a tile exceeds it
-// by more than 2^8 -- P <= 2^8 stays exact enough in bf16/fp32 and O / l is independent of the m that was used.
+// Forward on tcgen05: persistent CTAs; work item = 256 queries of one (head, trial) (two warpgroups, 128 rows each, one
+// thread per row), streaming 128-key tiles (K and V both as [keys][32] SW64 tiles; the P V MMAs read V MN-major).
+// Per tile and warpgroup g:
+//   S_g = Q_g K^T (2 MMAs, N = 128) -> TMEM;  thread: ONE sweep P = 2^(S c - m) against the stale running maximum m,
+//   row sum, bf16 pairs -> operand buffer in TMEM;  O_g += P V (8 TS-mode MMAs, N = 32) accumulating in TMEM.
+// The reference m is only re-established (row maximum pass, O / l rescaled) for the first visible tile of a row and when
+// the row sum shows that it has gone stale -- O / l is independent of the m that was used.
 // TMEM map: S_g at g*128 (128), P_g at 256 + g*64 (64), O_g at 384 + g*32 (32).
 // ================================================================================================
 constexpr int kFwdTileK = 128;
