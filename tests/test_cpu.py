@@ -97,3 +97,38 @@ def test_known_answers():
                                     n_heads=1, n_kv_heads=1))
     from oracle.brainformer_ref import to_patches
     assert torch.equal(small.to_patches(x), to_patches(x, 8))
+
+
+def test_label_rule_reproduces_the_reference_masks():
+    """The kernels never see a mask tensor: key j is visible to query i iff kid[j] <= qid[i] (ops.LabelMask).  Check on the
+    CPU that this rule gives exactly the three dense masks the reference builds: the block-causal mask
+    (brainformer.py:93-111, pinned by the golden mask(6, 2)), the MAE sub-matrix gathered at the kept positions
+    (brainformer.py:392-413) and the simple_mae padding mask (simple_mae:349-352)."""
+    from frankenstein_b200 import brainformer as bf
+    from oracle.brainformer_ref import block_causal_mask
+    b = torch.load(os.path.join(GOLD, "brainformer_small.pt"), weights_only=False)
+    # block causal: labels = position // tokens_per_time_step
+    for S, E in ((12, 2), (48, 16), (96, 32)):
+        ids = torch.arange(S) // E
+        rule = ids[None, :] <= ids[:, None]
+        assert torch.equal(rule, bf.build_advanced_causal_mask(S, E).bool())
+        assert torch.equal(rule, block_causal_mask(S, E).bool())
+    ids = torch.arange(6) // 2                                  # the reference's own 6-token, 2-per-step example
+    assert torch.equal((ids[None, :] <= ids[:, None]), b["mask_6_2"].bool())
+    # MAE: the reference gathers mask[idx][:, idx] per sample; the label rule gathers the labels instead
+    g = torch.Generator().manual_seed(0)
+    S, E, keep = 96, 16, 24
+    full = bf.build_advanced_causal_mask(S, E).bool()
+    for _ in range(4):
+        idx = torch.sort(torch.randperm(S, generator=g)[:keep])[0]
+        sub = full[idx][:, idx]
+        lab = idx // E
+        assert torch.equal(lab[None, :] <= lab[:, None], sub)
+    # padding: attend iff neither token is padded; kid = pad ? INT_MAX : 0, qid = pad ? -1 : 0
+    pad = torch.rand(3, 40, generator=g) < 0.3
+    big = torch.iinfo(torch.int32).max
+    kid = torch.where(pad, big, 0)
+    qid = torch.where(pad, -1, 0)
+    rule = kid[:, None, :] <= qid[:, :, None]
+    ref = (~pad)[:, :, None] & (~pad)[:, None, :]
+    assert torch.equal(rule, ref)
