@@ -132,3 +132,62 @@ def test_label_rule_reproduces_the_reference_masks():
     rule = kid[:, None, :] <= qid[:, :, None]
     ref = (~pad)[:, :, None] & (~pad)[:, None, :]
     assert torch.equal(rule, ref)
+
+
+def _packed_ema_worker(rank, world, port, q):
+    """One rank of the packed-buffer protocol of VectorQuantize._ema_step, with the rank-local statistics formed by plain
+    torch on the CPU (the kernels need a B200): [K*D embed_sum | K bins | R*D dead-code candidate rows]."""
+    import torch.distributed as dist
+    from frankenstein_b200.vector_quantize import dead_code_layout
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(5)
+    K, D, N = 12, 8, 40                                  # N rows per rank
+    X = torch.randn(world * N, D)
+    ind = torch.randint(0, K, (world * N,))
+    xr, ir = X[rank * N:(rank + 1) * N], ind[rank * N:(rank + 1) * N]
+    per_rank, R = dead_code_layout(K, N, world)
+    stats = torch.zeros(K * D + K + R * D)
+    stats[:K * D].view(K, D).index_add_(0, ir, xr)
+    stats[K * D:K * D + K].index_add_(0, ir, torch.ones(N))
+    rows = (torch.arange(per_rank) * 7 + rank) % N       # this rank's candidate rows (any deterministic choice)
+    tail = stats[K * D + K:].view(R, D)
+    tail[rank * per_rank:(rank + 1) * per_rank] = xr[rows]     # own slice only; the SUM gathers the slices
+    dist.all_reduce(stats)
+    q.put(stats.clone() if rank == 0 else None)
+    # every rank must hold the identical buffer (codebooks stay bit-identical without buffer broadcasts)
+    gathered = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(gathered, stats)
+    assert all(torch.equal(g, gathered[0]) for g in gathered)
+    dist.destroy_process_group()
+
+
+def test_packed_ema_allreduce_two_ranks_gloo():
+    """SURVEY 8e on the CPU: ONE all-reduce of the packed buffer carries embed_sum, bins and the dead-code candidates
+    (each rank writes only its slice of the tail); the result equals the single-process statistics of the concatenated
+    batch and the tail is the concatenation of the ranks' rows."""
+    import torch.multiprocessing as mp
+    from frankenstein_b200.vector_quantize import dead_code_layout
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 300
+    procs = [ctx.Process(target=_packed_ema_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=180) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    stats = next(g for g in got if g is not None)
+    torch.manual_seed(5)
+    K, D, N = 12, 8, 40
+    X = torch.randn(world * N, D)
+    ind = torch.randint(0, K, (world * N,))
+    per_rank, R = dead_code_layout(K, N, world)
+    assert R == per_rank * world and per_rank >= 1
+    es = torch.zeros(K, D).index_add_(0, ind, X)
+    bins = torch.zeros(K).index_add_(0, ind, torch.ones(world * N))
+    assert torch.allclose(stats[:K * D].view(K, D), es, atol=1e-6)
+    assert torch.equal(stats[K * D:K * D + K], bins)
+    tail = stats[K * D + K:].view(R, D)
+    for r in range(world):
+        rows = (torch.arange(per_rank) * 7 + r) % N
+        assert torch.equal(tail[r * per_rank:(r + 1) * per_rank], X[r * N:(r + 1) * N][rows])
