@@ -7,6 +7,7 @@ entry point raises.
 from __future__ import annotations
 
 import ctypes
+import functools
 import os
 import re
 from typing import Dict, List, Tuple
@@ -75,24 +76,50 @@ def check(rc: int, what: str) -> None:
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise FkError("frankenstein_b200 kernels run on a B200 (sm_100a) only; got a CPU tensor "
                           "(no CPU fallback exists)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise FkError(f"tensors of one kernel call live on different devices ({dev} and {t.device})")
 
 
-_device_checked = False
+def on_tensor_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current: the C entry points launch on the current
+    device and on the stream `stream()` reports for it, so a model that lives on cuda:1 works without the caller having
+    to `torch.cuda.set_device(1)` first (host-side caches of the library are keyed by the device ordinal)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        idx = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                idx = a.device.index
+                break
+        if idx is None or idx == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(idx):
+            return fn(*args, **kw)
+    return wrapper
+
+
+_device_checked = set()
 
 
 def require_device() -> None:
-    global _device_checked
-    if _device_checked:
-        return
+    """The CURRENT device must be a compute-capability 10.x part (checked once per device ordinal)."""
     if not torch.cuda.is_available():
         raise FkError("no CUDA device: frankenstein_b200 has no CPU fallback")
+    idx = torch.cuda.current_device()
+    if idx in _device_checked:
+        return
     if not lib().fk_device_ok():
         raise FkError("libfk_b200.so is compiled for sm_100a only and the current device is not compute capability 10.x")
-    _device_checked = True
+    _device_checked.add(idx)
 
 
 def ptr(t) -> int:
@@ -100,7 +127,26 @@ def ptr(t) -> int:
 
 
 def stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (ABI calls run under `on_tensor_device`)."""
     return torch.cuda.current_stream().cuda_stream
+
+
+# caller-owned counter words of the ABI (work hand-out of the persistent kernels, last-block reductions): zero on entry,
+# put back to zero by the kernel.  One set per (device, stream): launches on one stream are ordered, so they can share
+# the words; launches on different streams get different ones and may overlap freely.
+COUNTER_WORDS = 32
+CTR_VQ_FINISH, CTR_MASKED_L1, CTR_ATTN_FWD, CTR_ATTN_BWD, CTR_GEMM = 0, 1, 2, 4, 8
+_counter_sets = {}
+
+
+def counters(slot: int = 0) -> int:
+    """device pointer to counter word `slot` of the current (device, stream)."""
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    t = _counter_sets.get(key)
+    if t is None:
+        t = torch.zeros(COUNTER_WORDS, device=torch.device("cuda", key[0]), dtype=torch.int32)
+        _counter_sets[key] = t
+    return t.data_ptr() + 4 * slot
 
 
 def launch_count() -> int:

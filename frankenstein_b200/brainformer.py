@@ -93,7 +93,11 @@ def build_advanced_causal_mask(block_size, tok_per_time):
 
 
 def _linear_bf16(x, weight, bias=None):
-    return F.linear(x.to(BF16), weight.to(BF16), None if bias is None else bias.to(BF16))
+    """bf16 GEMM regardless of the caller's autocast dtype: the reference trainer runs fp16 autocast
+    (utils/train_utils.py:96), under which F.linear would re-cast the bf16 operands to fp16 and hand fp16 activations to
+    kernels that take bf16.  The compute dtype of this package is bf16 (fp32 accumulate) whatever autocast says."""
+    with torch.autocast("cuda", enabled=False):
+        return F.linear(x.to(BF16), weight.to(BF16), None if bias is None else bias.to(BF16))
 
 
 class MLP(nn.Module):
@@ -186,8 +190,8 @@ class CausalCrossAttention(nn.Module):
         # two projections instead of one fused [k|v] GEMM: slicing a fused buffer costs a zero-fill + strided copy per
         # slice in autograd (select_backward), more than the second GEMM launch
         ctx_bf16 = context.to(BF16)
-        k = F.linear(ctx_bf16, self.kw.weight.to(BF16)).view(B, S, self.n_heads, -1).transpose(1, 2)
-        v = F.linear(ctx_bf16, self.vw.weight.to(BF16)).view(B, S, self.n_heads, -1).transpose(1, 2)
+        k = _linear_bf16(ctx_bf16, self.kw.weight).view(B, S, self.n_heads, -1).transpose(1, 2)
+        v = _linear_bf16(ctx_bf16, self.vw.weight).view(B, S, self.n_heads, -1).transpose(1, 2)
         res = _dense_mask_attention(q, k, v, attn_mask)
         res = res.transpose(1, 2).reshape(B, T, -1)
         return _linear_bf16(res, self.project.weight)

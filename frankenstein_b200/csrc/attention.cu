@@ -696,6 +696,10 @@ FK_API int fk_rope(void* x, long long bs, long long ts, int B, int S, int H, int
   FK_REQUIRE(head_dim == kHD, "fk_rope: only head_dim 32 is built");
   FK_REQUIRE(x && table && B > 0 && S > 0 && H > 0 && P > 0, "fk_rope: bad argument");
   FK_REQUIRE(ts % 8 == 0 && bs % 8 == 0, "fk_rope: strides must keep 16-byte alignment");
+  // positions s + pos_offset must lie inside the table (e.g. more tokens than the rope cache holds would make the
+  // reference's rope[-T:] slice fail too); explicit positions are the caller's contract ([0, P)) and are clamped
+  FK_REQUIRE(pos != nullptr || (pos_offset >= 0 && static_cast<long long>(pos_offset) + S <= P),
+             "fk_rope: token positions pos_offset .. pos_offset + S - 1 fall outside the rope table");
   const long long total = static_cast<long long>(B) * S * H * 4;
   rope_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       static_cast<__nv_bfloat16*>(x), bs, ts, B, S, H, reinterpret_cast<const float2*>(table), P, pos, pos_offset, inverse);

@@ -21,6 +21,7 @@
 // TMA-loaded with the 64-byte swizzle.  The smem data pipe, which bounds an SS-mode version of this kernel, only
 // carries the streamed operands.
 #include "common.cuh"
+#include "fk_b200.h"
 #include "tma_host.cuh"
 
 namespace fk {
@@ -50,18 +51,18 @@ struct TcParams {
   const int* rope_pos;                                 // store of dK / dQ (position of row = rope_pos ? rope_pos[b][row]
   int rope_len, rope_offset;                           //  : row + rope_offset), replacing two fk_rope passes per layer
   long long* prof;                                     // kProf instantiation: [n_ctas][16] cycle counters
+  unsigned int* items;                                 // caller-owned hand-out counters of THIS launch: [0] next item,
+                                                       // [1] CTAs finished; zero on entry, zeroed again by the last CTA out
   int mn_major;                                        // 1: the accumulate MMAs read their B operand (Q / dO / K tile,
                                                        // [64 tokens][32 dims]) MN-major from the score stage itself;
                                                        // 0: K-major from transposed copies (tm_tA / tm_tB)
 };
 
-// Diagnosis only (scripts/gpu_attn_stalls.py): when a buffer is set, fk_attn_backward_tc launches the stall-accounting
+// Diagnosis only (scripts/gpu_attn_stalls.py): fk_attn_backward_tc_profile launches the stall-accounting
 // instantiation, which writes per CTA: 0 lifetime, 1 setup, 2 tiles, 3 first score stage ready, 4 sum wait sdp_full,
 // 5 (unused), 6 sum named barrier, 7 sum compute, 8 last p_ready, 9 accumulators complete, 10 stores done,
 // 11 score issuer wait st_full, 12 score issuer wait stage_free, 13 acc issuer wait p_ready, 14 producer wait st_empty
 // (3..10 by warpgroup 0, warp 4, lane 0; times since CTA start).
-static long long* g_attn_prof = nullptr;
-static int g_attn_prof_mode = 1;   // 1 = full stall accounting, 2 = light (lifetime + global timestamps + SM id)
 
 template <int kProf>
 __device__ __forceinline__ void wait_acc(uint64_t* bar, uint32_t phase, long long& acc) {
@@ -158,10 +159,10 @@ __device__ __forceinline__ void tmem_wait1_32(uint32_t (&a)[32]) {
                :: "memory");
 }
 
-// Work-item hand-out of the persistent backward kernels: [mode][0] = next item, [mode][1] = CTAs that have finished;
-// the last CTA to finish puts both back to zero, so no host-side reset (and no extra launch) is needed.  One launch per
-// mode at a time (the library is driven from one stream per process, like the rest of the ABI).
-__device__ unsigned int g_bwd_items[2][2];
+// Work-item hand-out of the persistent kernels: p.items[0] = next item, p.items[1] = CTAs that have finished; the last
+// CTA to finish puts both back to zero, so no host-side reset (and no extra launch) is needed.  The two words belong
+// to the caller (one pair per launch in flight: launches on different streams must be given different pairs), so the
+// library holds no device-side state and is re-entrant per stream.
 
 template <int MODE, int kProf>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -267,7 +268,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   };
   if (warp == 2) {
     int first = 0;
-    if (lane == 0) first = static_cast<int>(atomicAdd(&g_bwd_items[MODE][0], 1u));
+    if (lane == 0) first = static_cast<int>(atomicAdd(&p.items[0], 1u));
     first = __shfl_sync(0xffffffffu, first, 0);
     if (lane == 0) item_slot[0] = first;
     if (first < n_items) build_list(first, 0);
@@ -288,7 +289,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
 
   if (warp == 2) {
     int nxt = 0;
-    if (lane == 0) nxt = static_cast<int>(atomicAdd(&g_bwd_items[MODE][0], 1u));
+    if (lane == 0) nxt = static_cast<int>(atomicAdd(&p.items[0], 1u));
     nxt = __shfl_sync(0xffffffffu, nxt, 0);
     if (lane == 0) item_slot[(item_n + 1) & 1] = nxt;
     if (nxt < n_items) build_list(nxt, (item_n + 1) & 1);
@@ -659,9 +660,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   }
   if (threadIdx.x == 0) {
     // the last CTA out re-arms the hand-out for the next launch
-    if (atomicAdd(&g_bwd_items[MODE][1], 1u) == gridDim.x - 1) {
-      g_bwd_items[MODE][0] = 0u;
-      g_bwd_items[MODE][1] = 0u;
+    if (atomicAdd(&p.items[1], 1u) == gridDim.x - 1) {
+      p.items[0] = 0u;
+      p.items[1] = 0u;
       __threadfence();
     }
   }
@@ -727,7 +728,6 @@ struct FwdSmem {
   static constexpr int total = bars + 256;
 };
 
-__device__ unsigned int g_fwd_items[2];      // [0] next item, [1] CTAs finished (see g_bwd_items)
 
 struct FwdParams {
   const int *qid, *kid;
@@ -737,6 +737,7 @@ struct FwdParams {
   long long o_bs, o_ts;
   int B, H, Sq, Sk;
   float scale_log2;
+  unsigned int* items;                                  // caller-owned hand-out counters (see TcParams::items)
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
@@ -837,7 +838,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   int pre_cnt = -1;
   if (warp == 2) {
     int first = 0;
-    if (lane == 0) first = static_cast<int>(atomicAdd(&g_fwd_items[0], 1u));
+    if (lane == 0) first = static_cast<int>(atomicAdd(&p.items[0], 1u));
     first = __shfl_sync(0xffffffffu, first, 0);
     if (lane == 0) item_slot[0] = first;
     if (first < n_items) build_list(first, 0);
@@ -851,7 +852,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (warp == 2) {
     int nxt = 0;
-    if (lane == 0) nxt = static_cast<int>(atomicAdd(&g_fwd_items[0], 1u));
+    if (lane == 0) nxt = static_cast<int>(atomicAdd(&p.items[0], 1u));
     nxt = __shfl_sync(0xffffffffu, nxt, 0);
     if (lane == 0) item_slot[(item_n + 1) & 1] = nxt;
     if (nxt < n_items) build_list(nxt, (item_n + 1) & 1);
@@ -1141,9 +1142,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
   if (threadIdx.x == 0) {
     // the last CTA out re-arms the hand-out for the next launch
-    if (atomicAdd(&g_fwd_items[1], 1u) == gridDim.x - 1) {
-      g_fwd_items[0] = 0u;
-      g_fwd_items[1] = 0u;
+    if (atomicAdd(&p.items[1], 1u) == gridDim.x - 1) {
+      p.items[0] = 0u;
+      p.items[1] = 0u;
       __threadfence();
     }
   }
@@ -1168,22 +1169,7 @@ FK_API int fk_attn_transpose(const void* x, long long bs, long long ts, int B, i
   return FK_OK;
 }
 
-static int bwd_sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
-
-// Diagnosis only: route fk_attn_backward_tc to the stall-accounting instantiation (prof: int64 [n_ctas, 16]; null = off).
-FK_API int fk_attn_set_profile_buffer(long long* prof, int mode) {
-  g_attn_prof = prof;
-  g_attn_prof_mode = (mode == 2) ? 2 : 1;
-  return FK_OK;
-}
+static int bwd_sm_count() { return fk_sm_count(); }
 
 // parts: 2 = dK/dV (needs qt, dot), 4 = dQ (needs kt).  delta must already hold rowsum(dO * O) (fk_attn_backward parts=1).
 FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
@@ -1193,9 +1179,27 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
                                long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
                                long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
                                const int* kmin, const int* kmax, float scale, const float* rope_table, int rope_len,
-                               const int* rope_pos, int rope_offset, int parts, void* stream_) {
+                               const int* rope_pos, int rope_offset, int parts, unsigned int* counters, void* stream_) {
+  return fk_attn_backward_tc_profile(q, k, v, d_o, qt, kt, dot, Sp, lse, delta, dq, dk, dv, B, H, S, head_dim, q_bs, q_ts, k_bs,
+                                     k_ts, v_bs, v_ts, do_bs, do_ts, dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts, qid, kid, qmin,
+                                     qmax, kmin, kmax, scale, rope_table, rope_len, rope_pos, rope_offset, parts, counters,
+                                     nullptr, 0, stream_);
+}
+
+// Same launch; prof != NULL selects the stall-accounting instantiation (diagnosis only, scripts/gpu_attn_stalls.py):
+// prof_mode 1 = full stall accounting, 2 = light (lifetime + global timestamps + SM id).
+FK_API int fk_attn_backward_tc_profile(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
+                               const void* dot, int Sp, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+                               int B, int H, int S, int head_dim, long long q_bs, long long q_ts, long long k_bs,
+                               long long k_ts, long long v_bs, long long v_ts, long long do_bs, long long do_ts,
+                               long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
+                               long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
+                               const int* kmin, const int* kmax, float scale, const float* rope_table, int rope_len,
+                               const int* rope_pos, int rope_offset, int parts, unsigned int* counters, long long* g_attn_prof,
+                               int g_attn_prof_mode, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(head_dim == 32, "fk_attn_backward_tc: only head_dim 32 is built");
+  FK_REQUIRE(counters != nullptr, "fk_attn_backward_tc: counters (4 zero-initialised uint32, one set per launch in flight) is null");
   FK_REQUIRE(rope_table == nullptr || rope_len > 0, "fk_attn_backward_tc: rope_len must be positive with a rope table");
   FK_REQUIRE(q && k && v && d_o && lse && delta && B > 0 && H > 0 && S > 0, "fk_attn_backward_tc: bad argument");
   FK_REQUIRE((parts & ~6) == 0 && parts != 0, "fk_attn_backward_tc: parts is a bitmask of 2 (dK/dV) and 4 (dQ)");
@@ -1203,7 +1207,8 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
   FK_REQUIRE(qid == nullptr || (qmin && qmax && kmin && kmax), "fk_attn_backward_tc: label ranges missing");
   FK_REQUIRE((S + kCols - 1) / kCols <= kMaxTiles, "fk_attn_backward_tc: sequence too long");
   FK_REQUIRE(Sp >= S && Sp % 8 == 0, "fk_attn_backward_tc: Sp must be >= S and a multiple of 8");
-  static bool attr_set = false;
+  static bool attr_set_dev[FK_MAX_DEVICES];
+  bool& attr_set = attr_set_dev[fk_device_ordinal()];
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
         cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
@@ -1255,6 +1260,7 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.out1 = static_cast<__nv_bfloat16*>(dk); p.o1_bs = dk_bs; p.o1_ts = dk_ts;
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = g_attn_prof;
+    p.items = counters;
     p.mn_major = mn_major;
     p.rope_table = reinterpret_cast<const float2*>(rope_table); p.rope_pos = rope_pos; p.rope_len = rope_len; p.rope_offset = rope_offset;
     if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DKV, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
@@ -1270,6 +1276,7 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
     p.out0 = nullptr; p.out1 = static_cast<__nv_bfloat16*>(dq); p.o1_bs = dq_bs; p.o1_ts = dq_ts;
     p.B = B; p.H = H; p.S_row = S; p.S_col = S; p.Sq = S; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.prof = g_attn_prof;
+    p.items = counters + 2;
     p.mn_major = mn_major;
     p.rope_table = reinterpret_cast<const float2*>(rope_table); p.rope_pos = rope_pos; p.rope_len = rope_len; p.rope_offset = rope_offset;
     if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DQ, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
@@ -1286,15 +1293,18 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
 FK_API int fk_attn_forward_tc(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S,
                               int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
                               long long v_ts, long long o_bs, long long o_ts, const int* qid, const int* kid, const int* qmin,
-                              const int* qmax, const int* kmin, const int* kmax, float scale, void* stream_) {
+                              const int* qmax, const int* kmin, const int* kmax, float scale, unsigned int* counters,
+                              void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(head_dim == 32, "fk_attn_forward_tc: only head_dim 32 is built");
+  FK_REQUIRE(counters != nullptr, "fk_attn_forward_tc: counters (2 zero-initialised uint32, one pair per launch in flight) is null");
   FK_REQUIRE(q && k && v && out && B > 0 && H > 0 && S > 0, "fk_attn_forward_tc: bad argument");
   FK_REQUIRE((qid == nullptr) == (kid == nullptr), "fk_attn_forward_tc: qid and kid go together");
   FK_REQUIRE(qid == nullptr || (qmin && qmax && kmin && kmax), "fk_attn_forward_tc: label ranges missing");
   FK_REQUIRE((S + kFwdTileK - 1) / kFwdTileK <= kMaxTiles && S < (1 << 20), "fk_attn_forward_tc: sequence too long");
   FK_REQUIRE(o_ts % 8 == 0 && o_bs % 8 == 0, "fk_attn_forward_tc: output strides must keep 16-byte alignment");
-  static bool attr_set = false;
+  static bool attr_set_dev[FK_MAX_DEVICES];
+  bool& attr_set = attr_set_dev[fk_device_ordinal()];
   if (!attr_set) {
     if (cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::total) != cudaSuccess) {
       fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
@@ -1312,6 +1322,7 @@ FK_API int fk_attn_forward_tc(const void* q, const void* k, const void* v, void*
   p.qid = qid; p.kid = kid; p.qmin = qmin; p.qmax = qmax; p.kmin = kmin; p.kmax = kmax;
   p.out = static_cast<__nv_bfloat16*>(out); p.lse = lse; p.o_bs = o_bs; p.o_ts = o_ts;
   p.B = B; p.H = H; p.Sq = S; p.Sk = S; p.scale_log2 = scale * 1.4426950408889634f;
+  p.items = counters;
   // persistent CTAs: one per SM (or per work item when there are fewer), looping over (256-query block, head, trial) items
   const long long n_items = static_cast<long long>((S + 255) / 256) * H * B;
   FK_REQUIRE(n_items < (1ll << 31), "fk_attn_forward_tc: too many work items");

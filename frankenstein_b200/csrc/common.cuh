@@ -33,6 +33,11 @@
 
 void fk_set_last_error(const char* msg, const char* file, int line);
 void fk_count_launch(int n = 1);
+// Host-side caches are keyed by the CUDA device ordinal (a process may drive several GPUs): ordinal of the current
+// device clamped to [0, FK_MAX_DEVICES), and its SM count.
+#define FK_MAX_DEVICES 64
+int fk_device_ordinal();
+int fk_sm_count();
 
 namespace fk {
 

@@ -218,22 +218,105 @@ vq_finish_kernel(const FinishParams p) {
 
 // ------------------------------------------------------------------------------------------
 // K5: EMA statistics.  stats = [K*D embed_sum | K bins] (one packed buffer = one all-reduce).
+// A sort-free, atomic-free-on-data segmented sum keyed by the code index: the rows of each code are listed (counting
+// sort: integer histogram -> exclusive scan -> fill), and ONE WARP PER CODE adds its rows in ascending row order with
+// coalesced 16-byte loads, so embed_sum is bit-reproducible from run to run (fp32 atomics to [K, D] were not) and
+// needs neither a memset nor a read-modify-write of the [K, D] buffer.  Workspace: int [3*K + N].
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowsPerBlock * 32)
-vq_ema_stats_kernel(const float* __restrict__ xn, const long long* __restrict__ indices, long long N, int K, int D,
-                    float* __restrict__ stats) {
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256)
+vq_ema_count_kernel(const long long* __restrict__ indices, long long N, int K, int* __restrict__ count) {
+  const long long row = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (row >= N) return;
   const long long k = indices[row];
-  if (k < 0 || k >= K) return;
-  const float* xr = xn + row * D;
-  float* dst = stats + k * D;
-  for (int d = lane * 4; d < D; d += 128) {
-    const float4 x = *reinterpret_cast<const float4*>(xr + d);
-    atomicAdd(reinterpret_cast<float4*>(dst + d), x);   // one 16-byte reduction at L2
+  if (k >= 0 && k < K) atomicAdd(count + k, 1);          // integer: order independent
+}
+
+// single block: offs[k] = exclusive prefix of count; cursor[k] = 0
+__global__ void __launch_bounds__(1024)
+vq_ema_scan_kernel(const int* __restrict__ count, int K, int* __restrict__ offs, int* __restrict__ cursor) {
+  __shared__ int scan[1024];
+  const int per = (K + blockDim.x - 1) / blockDim.x;
+  const int k0 = min(K, static_cast<int>(threadIdx.x) * per), k1 = min(K, k0 + per);
+  int sum = 0;
+  for (int k = k0; k < k1; ++k) sum += count[k];
+  scan[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < blockDim.x; off <<= 1) {
+    const int v = (threadIdx.x >= off) ? scan[threadIdx.x - off] : 0;
+    __syncthreads();
+    scan[threadIdx.x] += v;
+    __syncthreads();
   }
-  if (lane == 0) atomicAdd(stats + static_cast<long long>(K) * D + k, 1.f);
+  int run = scan[threadIdx.x] - sum;
+  for (int k = k0; k < k1; ++k) {
+    offs[k] = run;
+    cursor[k] = 0;
+    run += count[k];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+vq_ema_fill_kernel(const long long* __restrict__ indices, long long N, int K, const int* __restrict__ offs,
+                   int* __restrict__ cursor, int* __restrict__ list) {
+  const long long row = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (row >= N) return;
+  const long long k = indices[row];
+  if (k >= 0 && k < K) list[offs[k] + atomicAdd(cursor + k, 1)] = static_cast<int>(row);   // any order; sorted below
+}
+
+// one warp per code: rows in ascending order (the canonical order that makes the fp32 sum reproducible)
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+vq_ema_segsum_kernel(const float* __restrict__ xn, const int* __restrict__ count, const int* __restrict__ offs,
+                     const int* __restrict__ list, int K, int D, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (k >= K) return;
+  const int c = count[k];
+  const int* seg = list + offs[k];
+  float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // D <= 256: 2 float4 per lane
+  auto add_row = [&](int row) {
+    const float* xr = xn + static_cast<long long>(row) * D;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int d = lane * 4 + i * 128;
+      if (d < D) {
+        const float4 x = ldg_nc_f4(xr + d);
+        acc[i].x += x.x; acc[i].y += x.y; acc[i].z += x.z; acc[i].w += x.w;
+      }
+    }
+  };
+  if (c <= 32) {
+    // rank sort inside the warp: lane i holds one row id; the lane whose rank is t supplies the t-th row
+    const int id = lane < c ? seg[lane] : 0x7fffffff;
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) rank += (__shfl_sync(0xffffffffu, id, j) < id) ? 1 : 0;
+    for (int t = 0; t < c; ++t) {
+      const unsigned m = __ballot_sync(0xffffffffu, rank == t && lane < c);
+      add_row(__shfl_sync(0xffffffffu, id, __ffs(m) - 1));
+    }
+  } else {
+    // long segment (a hot code): repeatedly take the smallest row id above the last one added
+    int last = -1;
+    for (int t = 0; t < c; ++t) {
+      int best = 0x7fffffff;
+      for (int j = lane; j < c; j += 32) {
+        const int v = seg[j];
+        best = (v > last && v < best) ? v : best;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      add_row(best);
+      last = best;
+    }
+  }
+  float* dst = stats + static_cast<long long>(k) * D;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int d = lane * 4 + i * 128;
+    if (d < D) *reinterpret_cast<float4*>(dst + d) = acc[i];
+  }
+  if (lane == 0) stats[static_cast<long long>(K) * D + k] = static_cast<float>(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -524,15 +607,28 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_finish(const float* 
 
 extern "C" __attribute__((visibility("default"))) long long fk_vq_finish_partials(long long N) { return (N + kRowsPerBlock - 1) / kRowsPerBlock; }
 
+extern "C" __attribute__((visibility("default"))) long long fk_vq_ema_stats_ws(long long N, int K) {
+  return 3ll * K + N;      // int32 words: count | offs | cursor | row list
+}
+
 extern "C" __attribute__((visibility("default"))) int fk_vq_ema_stats(const float* xn, const long long* indices, long long N, int K, int D, float* stats,
-                               void* stream_) {
+                               int* ws, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  FK_REQUIRE(N > 0 && K > 0 && D > 0 && D % 4 == 0, "fk_vq_ema_stats: bad shape (D % 4 == 0)");
-  FK_REQUIRE(xn && indices && stats, "fk_vq_ema_stats: null pointer");
-  if (cudaMemsetAsync(stats, 0, (static_cast<size_t>(K) * D + K) * sizeof(float), stream) != cudaSuccess) return FK_ERR_CUDA;
-  vq_ema_stats_kernel<<<row_blocks(N), kRowsPerBlock * 32, 0, stream>>>(xn, indices, N, K, D, stats);
+  FK_REQUIRE(N > 0 && N < (1ll << 31) && K > 0 && K <= (1 << 20) && D > 0 && D % 4 == 0 && D <= 256,
+             "fk_vq_ema_stats: bad shape (D % 4 == 0, D <= 256, K <= 2^20)");
+  FK_REQUIRE(xn && indices && stats && ws, "fk_vq_ema_stats: null pointer");
+  int *count = ws, *offs = ws + K, *cursor = ws + 2 * static_cast<long long>(K), *list = ws + 3 * static_cast<long long>(K);
+  if (cudaMemsetAsync(count, 0, static_cast<size_t>(K) * sizeof(int), stream) != cudaSuccess) return FK_ERR_CUDA;
+  const unsigned nb = static_cast<unsigned>((N + 255) / 256);
+  vq_ema_count_kernel<<<nb, 256, 0, stream>>>(indices, N, K, count);
   FK_CHECK_LAUNCH();
-  fk_count_launch(2);
+  vq_ema_scan_kernel<<<1, 1024, 0, stream>>>(count, K, offs, cursor);
+  FK_CHECK_LAUNCH();
+  vq_ema_fill_kernel<<<nb, 256, 0, stream>>>(indices, N, K, offs, cursor, list);
+  FK_CHECK_LAUNCH();
+  vq_ema_segsum_kernel<<<(K + kRowsPerBlock - 1) / kRowsPerBlock, kRowsPerBlock * 32, 0, stream>>>(xn, count, offs, list, K, D, stats);
+  FK_CHECK_LAUNCH();
+  fk_count_launch(5);
   return FK_OK;
 }
 

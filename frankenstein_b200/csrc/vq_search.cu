@@ -369,15 +369,7 @@ vq_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
+static int sm_count() { return fk_sm_count(); }
 
 }  // namespace fk
 
@@ -463,7 +455,8 @@ static int search_launch(const void* x_bf16, const void* cb_bf16, const float* c
   p.nstage = nstage;
   const int smem_bytes = fixed + nstage * kBSlabBytes;
 
-  static bool attr_set = false;
+  static bool attr_set_dev[FK_MAX_DEVICES];
+  bool& attr_set = attr_set_dev[fk_device_ordinal()];
   if (!attr_set) {
     if (cudaFuncSetAttribute(vq_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
         cudaFuncSetAttribute(vq_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess) {

@@ -10,7 +10,8 @@ from typing import Optional
 
 import torch
 
-from ._lib import FkError, check, lib, ptr, require_cuda, require_device, stream, timed
+from . import _lib
+from ._lib import FkError, check, counters, lib, on_tensor_device, ptr, require_cuda, require_device, stream, timed
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
@@ -29,6 +30,7 @@ ATTN_BWD_OPERANDS = os.environ.get("FK_ATTN_BWD_OPERANDS", "mn")
 # ------------------------------------------------------------------------------------------------
 class _NormFn(torch.autograd.Function):
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, weight, bias, eps, rms, out_dtype):
         require_cuda(x, weight)
         require_device()
@@ -52,6 +54,7 @@ class _NormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g):
         xc, w, mean, rstd = ctx.saved_tensors
         D = xc.shape[-1]
@@ -79,6 +82,7 @@ class _AddNormFn(torch.autograd.Function):
     backward with the residual-gradient add and emits the bf16 gradient of the delta branch."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, delta, weight, bias, eps, rms, out_dtype):
         require_cuda(x, delta, weight)
         require_device()
@@ -107,6 +111,7 @@ class _AddNormFn(torch.autograd.Function):
         return x_new, y
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g_xnew, g_y):
         x_new, w, mean, rstd = ctx.saved_tensors
         D = x_new.shape[-1]
@@ -155,6 +160,7 @@ def rms_norm(x, weight, eps=1e-6, out_dtype=torch.bfloat16):
 # ------------------------------------------------------------------------------------------------
 class _SwiGLUFn(torch.autograd.Function):
     @staticmethod
+    @on_tensor_device
     def forward(ctx, h13):
         require_cuda(h13)
         require_device()
@@ -169,6 +175,7 @@ class _SwiGLUFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, gy):
         (h13,) = ctx.saved_tensors
         H = h13.shape[-1] // 2
@@ -201,6 +208,7 @@ class LabelMask:
             self.kmin, self.kmax = self._ranges(self.kid)
 
     @staticmethod
+    @on_tensor_device
     def _ranges(ids):
         B, S = ids.shape
         nt = (S + 63) // 64
@@ -244,6 +252,7 @@ class RopeSpec:
         return RopeSpec(table, None, cache.shape[0] - T if last else 0)
 
 
+@on_tensor_device
 def _rope_inplace(x4, spec: RopeSpec, inverse: bool):
     """x4: bf16 view [B, S, H, 32] (token stride arbitrary, head stride 32)."""
     B, S, H, hd = x4.shape
@@ -256,10 +265,12 @@ def _rope_inplace(x4, spec: RopeSpec, inverse: bool):
 # attention on the fused QKV projection
 # ------------------------------------------------------------------------------------------------
 _BWD_PARTS = (2, 4)     # diagnosis hook (scripts/gpu_attn_stalls.py profiles one backward kernel at a time)
+_BWD_PROFILE = None     # diagnosis hook: (int64 counter tensor, mode) -> fk_attn_backward_tc_profile
 
 
 class _AttnQKVFn(torch.autograd.Function):
     @staticmethod
+    @on_tensor_device
     def forward(ctx, qkv, n_heads, rope, mask, scale):
         """qkv: bf16 [B, S, 3*H*32] fresh output of the fused projection (q|k|v); RoPE is applied in place."""
         require_cuda(qkv)
@@ -289,13 +300,17 @@ class _AttnQKVFn(torch.autograd.Function):
             with timed("attn_fwd"):
                 check(lib().fk_attn_forward_tc(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, hd,
                                                q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
-                                               out.stride(0), out.stride(1), *margs, stream()), "fk_attn_forward_tc")
+                                               out.stride(0), out.stride(1), *margs, counters(_lib.CTR_ATTN_FWD), stream()),
+                      "fk_attn_forward_tc")
+        if rope is not None:
+            ctx.mark_dirty(qkv)          # q and k were rotated in place: autograd's version counter must see the write
         ctx.save_for_backward(qkv, out, lse)
         ctx.rope, ctx.mask, ctx.scale, ctx.H = rope, mask, scale, H
-        return out
+        return out, (qkv if rope is not None else None)
 
     @staticmethod
-    def backward(ctx, d_o):
+    @on_tensor_device
+    def backward(ctx, d_o, _d_qkv_rotated=None):
         qkv, out, lse = ctx.saved_tensors
         B, S, W = qkv.shape
         H = ctx.H
@@ -343,13 +358,17 @@ class _AttnQKVFn(torch.autograd.Function):
             for name, part in (("attn_bwd_dkv", 2), ("attn_bwd_dq", 4)):
                 if part not in _BWD_PARTS:
                     continue
+                args = (ptr(q), ptr(k), ptr(v), ptr(d4), ptr(tr["q"]), ptr(tr["k"]), ptr(tr["do"]), Sp,
+                        ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv), B, H, S, hd,
+                        q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                        d4.stride(0), d4.stride(1), dq.stride(0), dq.stride(1), dk.stride(0),
+                        dk.stride(1), dv.stride(0), dv.stride(1), *common, *rope_args, part, counters(_lib.CTR_ATTN_BWD))
                 with timed(name):
-                    check(lib().fk_attn_backward_tc(ptr(q), ptr(k), ptr(v), ptr(d4), ptr(tr["q"]), ptr(tr["k"]), ptr(tr["do"]), Sp,
-                                                    ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv), B, H, S, hd,
-                                                    q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
-                                                    d4.stride(0), d4.stride(1), dq.stride(0), dq.stride(1), dk.stride(0),
-                                                    dk.stride(1), dv.stride(0), dv.stride(1), *common, *rope_args, part, stream()),
-                          "fk_attn_backward_tc")
+                    if _BWD_PROFILE is not None:
+                        check(lib().fk_attn_backward_tc_profile(*args, ptr(_BWD_PROFILE[0]), int(_BWD_PROFILE[1]), stream()),
+                              "fk_attn_backward_tc_profile")
+                    else:
+                        check(lib().fk_attn_backward_tc(*args, stream()), "fk_attn_backward_tc")
             rope_done = True                          # dq / dk were rotated back inside the kernels
         if ctx.rope is not None and not rope_done:
             _rope_inplace(dq, ctx.rope, True)
@@ -365,4 +384,4 @@ def attention_qkv(qkv, n_heads: int, rope: Optional[RopeSpec] = None, mask: Opti
         raise FkError("the attention kernel is built for head_dim 32")
     if scale is None:
         scale = hd ** -0.5
-    return _AttnQKVFn.apply(qkv, n_heads, rope, mask, scale)
+    return _AttnQKVFn.apply(qkv, n_heads, rope, mask, scale)[0]

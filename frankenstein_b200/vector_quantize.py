@@ -22,7 +22,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import _lib
-from ._lib import DTYPE_CODE, FkError, check, lib, ptr, require_cuda, require_device, stream, timed
+from ._lib import DTYPE_CODE, FkError, check, counters, lib, on_tensor_device, ptr, require_cuda, require_device, stream, timed
 
 BN = 128  # code tile of the search kernel (c2 padding granularity)
 CAND = 4  # candidates per (row, slot) written by the search kernel
@@ -35,6 +35,7 @@ def _round_up(a: int, b: int) -> int:
 # ------------------------------------------------------------------------------------------------
 # thin functional wrappers over the C ABI (tensors in, tensors out)
 # ------------------------------------------------------------------------------------------------
+@on_tensor_device
 def prepare_input(e: torch.Tensor, use_cosine: bool):
     """e [N, D] (f32/bf16/f16, contiguous) -> (xn fp32 [N, D], x_bf16 [N, Dp], inv_norm [N] | None)."""
     require_cuda(e)
@@ -52,6 +53,7 @@ def prepare_input(e: torch.Tensor, use_cosine: bool):
     return xn, xb, inv_norm
 
 
+@on_tensor_device
 def prepare_codebook(embed: torch.Tensor, use_cosine: bool, cb: Optional[torch.Tensor] = None,
                      c2pad: Optional[torch.Tensor] = None):
     require_cuda(embed)
@@ -67,6 +69,7 @@ def prepare_codebook(embed: torch.Tensor, use_cosine: bool, cb: Optional[torch.T
     return cb, c2pad
 
 
+@on_tensor_device
 def search(xb: torch.Tensor, cb: torch.Tensor, c2pad: torch.Tensor, K: int, use_cosine: bool, max_ctas: int = 0):
     """tcgen05 search -> (cand_val [N,S,4] fp32 keys, cand_idx [N,S,4] int32 code indices, -1 = none)."""
     require_cuda(xb, cb, c2pad)
@@ -85,16 +88,7 @@ def search(xb: torch.Tensor, cb: torch.Tensor, c2pad: torch.Tensor, K: int, use_
     return cand_val, cand_idx
 
 
-_counters = {}
-
-
-def _counter(device) -> torch.Tensor:
-    key = (device.type, device.index)
-    if key not in _counters:
-        _counters[key] = torch.zeros(4, device=device, dtype=torch.int32)
-    return _counters[key]
-
-
+@on_tensor_device
 def finish(xn, embed, cand_val, cand_idx, use_cosine: bool, training: bool, commitment_weight: float,
            want_quantize: bool = True):
     """exact re-score + gather (+ straight-through, commitment loss) -> (indices int64 [N], quantize, loss [1])."""
@@ -108,15 +102,17 @@ def finish(xn, embed, cand_val, cand_idx, use_cosine: bool, training: bool, comm
     partials = torch.empty(lib().fk_vq_finish_partials(N), device=xn.device, dtype=torch.float32) if training else None
     check(lib().fk_vq_finish(ptr(xn), ptr(embed), ptr(cand_val), ptr(cand_idx), N, K, D, S, int(use_cosine),
                              int(training), float(commitment_weight), ptr(indices), ptr(quantize), ptr(loss),
-                             ptr(partials), ptr(_counter(xn.device)), stream()), "fk_vq_finish")
+                             ptr(partials), counters(_lib.CTR_VQ_FINISH), stream()), "fk_vq_finish")
     return indices, quantize, loss
 
 
+@on_tensor_device
 def ema_stats(xn, indices, K: int, extra_rows: int = 0) -> torch.Tensor:
     """packed [K*D + K (+ extra_rows*D)] fp32 = embed_sum || bins (|| room for dead-code candidates)."""
     N, D = xn.shape
     stats = torch.empty(K * D + K + extra_rows * D, device=xn.device, dtype=torch.float32)
-    check(lib().fk_vq_ema_stats(ptr(xn), ptr(indices), N, K, D, ptr(stats), stream()), "fk_vq_ema_stats")
+    ws = torch.empty(lib().fk_vq_ema_stats_ws(N, K), device=xn.device, dtype=torch.int32)
+    check(lib().fk_vq_ema_stats(ptr(xn), ptr(indices), N, K, D, ptr(stats), ptr(ws), stream()), "fk_vq_ema_stats")
     return stats
 
 
@@ -131,6 +127,7 @@ class _VQFunction(torch.autograd.Function):
     """(quantize_out, indices, loss) = f(x); backward = fk_vq_backward (STE + commitment term + normalize Jacobian)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, vq):
         quantize, indices, loss, xn, inv_norm = vq._forward_impl(x)
         ctx.vq = vq
@@ -142,6 +139,7 @@ class _VQFunction(torch.autograd.Function):
         return quantize.view(x.shape), indices, loss
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g_q, _g_ind, g_loss):
         xn, quantize, inv_norm = ctx.saved_tensors
         vq = ctx.vq
@@ -206,10 +204,33 @@ class VectorQuantize(nn.Module):
         # test hooks: inject the draws upstream takes from the global RNG
         self.sample_rows_override = None     # int64 [>=R] rows used for dead-code replacement
         self.kmeans_init_override = None     # int64 [K] rows used as initial k-means means
-        self.register_load_state_dict_post_hook(lambda m, k: m._mark_dirty())
+        # data-parallel EMA: the all-reduce of the packed statistics and the finalize kernels run on a side stream and
+        # overlap the decoder forward and the whole backward (the updated codebook is first needed by the
+        # NEXT step's search); the main stream only waits for them when the codebook is touched again.
+        # True = when the statistics are all-reduced (world > 1), "always" = also on one GPU (tests), False = in stream.
+        self.overlap_ema = True
+        self._side_stream = None
+        self._pending = None         # (event, tensors kept alive until the side stream has consumed them)
+        self.register_load_state_dict_post_hook(VectorQuantize._after_load)
+        self.register_state_dict_pre_hook(VectorQuantize._before_state_dict)
 
     # ---- operand cache ----------------------------------------------------------------------
+    @staticmethod
+    def _after_load(module, incompatible_keys):      # (a plain function, not a lambda: the module stays picklable)
+        module._mark_dirty()
+
+    @staticmethod
+    def _before_state_dict(module, prefix, keep_vars):
+        module._wait_pending()
+
+    def _wait_pending(self):
+        """Make the current stream wait for an EMA update still running on the side stream."""
+        if self._pending is not None:
+            torch.cuda.current_stream().wait_event(self._pending[0])
+            self._pending = None
+
     def _mark_dirty(self):
+        self._wait_pending()
         self._operand_dirty = True
         self._kmeans_initted_host = None      # re-read `initted` from the buffer
 
@@ -218,6 +239,7 @@ class VectorQuantize(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def _operands(self):
+        self._wait_pending()
         embed = self._codebook.embed[0]
         if self._operand_dirty or self._cb is None or self._cb.device != embed.device:
             self._cb, self._c2pad = prepare_codebook(embed.contiguous(), self.use_cosine_sim)
@@ -226,6 +248,7 @@ class VectorQuantize(nn.Module):
 
     @property
     def codebook(self):
+        self._wait_pending()
         return self._codebook.embed[0]
 
     def _sync(self) -> bool:
@@ -298,6 +321,7 @@ class VectorQuantize(nn.Module):
         K, D = self.codebook_size, self.dim
         flat = x.detach().reshape(-1, D).contiguous()
         training = self.training
+        self._wait_pending()             # the previous step's EMA update (side stream) must have landed
         xn, xb, inv_norm = prepare_input(flat, self.use_cosine_sim)
         if not self._is_initted():
             self._kmeans_init(xn, xb)
@@ -309,6 +333,7 @@ class VectorQuantize(nn.Module):
             self._ema_step(xn, indices)     # after the gather: the search/gather use the pre-update codebook
         return quantize, indices, loss, xn, inv_norm
 
+    @on_tensor_device
     def forward(self, x: torch.Tensor):
         require_cuda(x)
         require_device()
@@ -342,18 +367,76 @@ class VectorQuantize(nn.Module):
                 tail.zero_()
             rows = self._sample_rows(N, per_rank, xn.device)
             torch.index_select(xn, 0, rows, out=tail[rank * per_rank:(rank + 1) * per_rank])
-        if sync:
-            dist.all_reduce(stats)
-        self.last_bins = stats[K * D:K * D + K]
         ws_total = torch.empty(1, device=xn.device, dtype=torch.float32)
         ws_rank = torch.empty(K, device=xn.device, dtype=torch.int32)
         n_exp = torch.empty(1, device=xn.device, dtype=torch.int32)
         ar = torch.arange(R, device=xn.device, dtype=torch.int64) if R > 0 else None
         if self._cb is None or self._cb.device != xn.device:
             self._operands()
-        check(lib().fk_vq_ema_update(ptr(stats), ptr(cbk.cluster_size), ptr(cbk.embed_avg), ptr(cbk.embed), K, D, Dp, Kpad,
-                                     int(self.use_cosine_sim), self.decay, self.eps, thr, ptr(ar), R, ptr(tail), R,
-                                     ptr(self._cb), ptr(self._c2pad), ptr(ws_total), ptr(ws_rank), ptr(n_exp), stream()),
-              "fk_vq_ema_update")
+
+        def finalize():
+            if sync:
+                dist.all_reduce(stats)
+            check(lib().fk_vq_ema_update(ptr(stats), ptr(cbk.cluster_size), ptr(cbk.embed_avg), ptr(cbk.embed), K, D, Dp, Kpad,
+                                         int(self.use_cosine_sim), self.decay, self.eps, thr, ptr(ar), R, ptr(tail), R,
+                                         ptr(self._cb), ptr(self._c2pad), ptr(ws_total), ptr(ws_rank), ptr(n_exp), stream()),
+                  "fk_vq_ema_update")
+
+        if self.overlap_ema == "always" or (self.overlap_ema and sync):
+            if self._side_stream is None or self._side_stream.device != xn.device:
+                self._side_stream = torch.cuda.Stream(device=xn.device)
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)                       # statistics + candidate rows complete; gather/finish have read embed
+            with torch.cuda.stream(self._side_stream):
+                self._side_stream.wait_event(ready)
+                finalize()
+                done = torch.cuda.Event()
+                done.record(self._side_stream)
+            # the buffers were allocated on the main stream: keep them referenced until the main stream has waited on
+            # `done` (so the caching allocator cannot hand them out while the side stream still uses them)
+            self._pending = (done, (stats, tail, ws_total, ws_rank, n_exp, ar))
+        else:
+            finalize()
+        self.last_bins = stats[K * D:K * D + K]
         self.last_n_expired = n_exp
         self._operand_dirty = False
+
+
+class ResidualVQ(nn.Module):
+    """``vector_quantize_pytorch.ResidualVQ`` (imported next to VectorQuantize at models/vq_brain.py:6, never wired by the
+    reference): ``num_quantizers`` VectorQuantize layers applied greedily to the running residual.
+
+    forward(x [B,N,D]) -> (quantized_out [B,N,D] = sum of the layers' outputs, indices [B,N,Q] int64, losses [1,Q]), as
+    upstream: ``residual -= quantized.detach()`` between layers, so every layer's straight-through / commitment gradient
+    reaches x and each layer keeps its own EMA codebook.  Every layer is the sm_100a search / finish / EMA path above.
+    """
+
+    def __init__(self, *, dim, num_quantizers, codebook_size, shared_codebook=False, **kwargs):
+        super().__init__()
+        self.num_quantizers = num_quantizers
+        self.layers = nn.ModuleList([VectorQuantize(dim=dim, codebook_size=codebook_size, **kwargs)
+                                     for _ in range(num_quantizers)])
+        if shared_codebook:
+            first = self.layers[0]._codebook
+            for layer in self.layers[1:]:
+                layer._codebook = first
+
+    @property
+    def codebooks(self):
+        return torch.stack([layer.codebook for layer in self.layers], dim=0)
+
+    def get_codes_from_indices(self, indices):
+        """[B,N,Q] -> [Q,B,N,D] codewords."""
+        return torch.stack([layer.codebook[indices[..., q]] for q, layer in enumerate(self.layers)], dim=0)
+
+    def forward(self, x):
+        quantized_out, residual = None, x
+        all_indices, all_losses = [], []
+        for layer in self.layers:
+            quantized, indices, loss = layer(residual)
+            residual = residual - quantized.detach()
+            quantized_out = quantized if quantized_out is None else quantized_out + quantized
+            all_indices.append(indices)
+            all_losses.append(loss)
+        return quantized_out, torch.stack(all_indices, dim=-1), torch.stack(all_losses, dim=-1)

@@ -20,8 +20,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ._lib import DTYPE_CODE, FkError, check, lib, ptr, require_cuda, require_device, stream
-from .vector_quantize import VectorQuantize, _counter
+from . import _lib
+from ._lib import DTYPE_CODE, FkError, check, counters, lib, on_tensor_device, ptr, require_cuda, require_device, stream
+from .vector_quantize import VectorQuantize
 
 
 class CausalConv1d(nn.Conv1d):
@@ -170,6 +171,7 @@ class _MaskedL1(torch.autograd.Function):
     """custom_l1_loss (models/vq_brain.py:220-227) as one fused forward and one fused backward kernel."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, pred, gt):
         require_cuda(pred, gt)
         require_device()
@@ -188,11 +190,12 @@ class _MaskedL1(torch.autograd.Function):
         loss = torch.empty(1, device=dev, dtype=torch.float32)
         denom = torch.empty(1, device=dev, dtype=torch.float32)
         check(lib().fk_masked_l1_forward(ptr(p), DTYPE_CODE[p.dtype], ptr(g), R, C, ptr(row_valid), ptr(ps), ptr(pc),
-                                         ptr(_counter(dev)[1:]), ptr(loss), ptr(denom), stream()), "fk_masked_l1_forward")
+                                         counters(_lib.CTR_MASKED_L1), ptr(loss), ptr(denom), stream()), "fk_masked_l1_forward")
         ctx.save_for_backward(p, g, row_valid, denom)
         return loss.view(())
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, g_loss):
         p, g, row_valid, denom = ctx.saved_tensors
         B, T, C = p.shape
@@ -203,6 +206,7 @@ class _MaskedL1(torch.autograd.Function):
         return grad.to(ctx.pred_dtype), None
 
 
+@on_tensor_device
 def perplexity(indices: torch.Tensor, codebook_size: int) -> torch.Tensor:
     """calculate_perp (models/vq_brain.py:238-243) from the code histogram."""
     require_cuda(indices)

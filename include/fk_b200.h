@@ -3,7 +3,10 @@
  * Conventions:
  *  - plain pointers and sizes, no torch types; all pointers are DEVICE pointers unless stated;
  *  - the caller owns every buffer (kernels never allocate or free);
- *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no implicit sync;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no implicit sync, and launches on the
+ *    CURRENT device (the caller selects the device its pointers live on; host-side caches are per device ordinal);
+ *  - no device-side global state: hand-out / last-block counters are caller-owned words (zero on entry, zero on exit),
+ *    so calls are re-entrant per stream;
  *  - return value: 0 = ok, negative = error (fk_last_error() has the text);
  *    -1 bad argument, -2 CUDA launch error, -3 unsupported shape, -4 driver entry point missing;
  *  - no CPU path exists: without a Blackwell GPU every compute entry point fails.
@@ -69,8 +72,11 @@ int fk_vq_finish(const float* xn, const float* embed, const float* cand_val, con
 /* ---- VQ: EMA statistics, EMA finalize + dead-code reset -------------------------------------- */
 /* Replaces `bins = onehot.sum()` and `embed_sum = einsum('h n d, h n c -> h c d')`.
  * stats: fp32 [K*D + K] = embed_sum || bins, one packed buffer so data-parallel ranks need ONE
- * all-reduce (zeroed inside the call). */
-int fk_vq_ema_stats(const float* xn, const long long* indices, long long N, int K, int D, float* stats,
+ * all-reduce (every element is written by the call).  Segmented sum keyed by the code index: counting sort of the
+ * rows, then one warp per code adds its rows in ascending row order (coalesced 16-byte loads, no atomics on data), so
+ * the result is bit-reproducible.  ws: int32 [fk_vq_ema_stats_ws(N, K)] scratch.  D <= 256. */
+long long fk_vq_ema_stats_ws(long long N, int K);
+int fk_vq_ema_stats(const float* xn, const long long* indices, long long N, int K, int D, float* stats, int* ws,
                     void* stream);
 /* Replaces ema_inplace x2, laplace_smoothing, `embed.copy_`, (cosine) l2norm and expire_codes_/
  * replace; also writes the next search's operand.  sample_rows (nullable): int64 [n_sample] rows of
@@ -138,18 +144,15 @@ int fk_attn_backward(const void* q, const void* k, const void* v, const void* o,
                      long long dk_bs, long long dk_ts, long long dv_bs, long long dv_ts, const int* qid, const int* kid,
                      const int* qmin, const int* qmax, const int* kmin, const int* kmax, float scale, int parts, void* stream);
 
-/* Diagnosis only (scripts/gpu_attn_stalls.py): while a buffer is set, fk_attn_backward_tc launches a stall-accounting
- * build of the same kernel that writes int64 [n_ctas, 24] cycle counters (see attention_tc.cu); null switches it off. */
-int fk_attn_set_profile_buffer(long long* prof, int mode);   /* mode 1 = full stall accounting, 2 = lifetime + %globaltimer + %smid only */
-
 /* tcgen05 / TMEM / TMA version of the attention backward (attention_tc.cu).  qt = kt = dot = NULL (default): the
  * contractions over tokens read the Q / dO / K tiles MN-major straight from the strided inputs.  Cross-check mode:
  * fk_attn_transpose makes [B][H][32][Sp] copies (zero padded, Sp % 8 == 0) that serve as K-major operands instead:
  * qt, dot for dK/dV (parts & 2), kt for dQ (parts & 4).  delta must already hold rowsum(dO*O)
  * (fk_attn_backward with parts = 1).  Same labels / ranges / strides conventions as fk_attn_backward; Sq == Sk == S.
- * The kernels are persistent (one CTA per SM taking work items from a device-side counter that re-arms itself at the end
- * of a launch): like the rest of this ABI they are meant to be driven from ONE stream per process; two launches of the
- * same part running concurrently on different streams would share the counter. */
+ * The kernels are persistent (one CTA per SM taking work items from a hand-out counter).  The counter words belong to
+ * the CALLER: `counters` = 4 uint32 (2 per part), zero on entry; the last CTA of a launch puts them back to zero, so the
+ * same words can serve every launch on one stream, and launches that may overlap (different streams / graph branches) must
+ * be given different words.  The library itself holds no device-side state: every entry point is re-entrant per stream. */
 int fk_attn_transpose(const void* x, long long bs, long long ts, int B, int S, int H, int head_dim, void* xt, int Sp,
                       void* stream);
 int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
@@ -161,14 +164,29 @@ int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void*
                         const int* kmin, const int* kmax, float scale,
                         const float* rope_table /* [rope_len][16][2] (cos, sin) or NULL: dq / dk are rotated back (the gradient of
                                                    apply_rope, brainformer.py:70-91) inside the kernel */,
-                        int rope_len, const int* rope_pos /* [B][S] or NULL */, int rope_offset, int parts, void* stream);
+                        int rope_len, const int* rope_pos /* [B][S] or NULL */, int rope_offset, int parts,
+                        unsigned int* counters, void* stream);
+/* Diagnosis only (scripts/gpu_attn_stalls.py): the same launch through a stall-accounting build of the kernel that writes
+ * int64 [n_items, 24] cycle counters to prof (see attention_tc.cu); prof_mode 1 = full stall accounting, 2 = lifetime +
+ * %globaltimer + %smid only.  prof == NULL behaves exactly like fk_attn_backward_tc. */
+int fk_attn_backward_tc_profile(const void* q, const void* k, const void* v, const void* d_o, const void* qt,
+                                const void* kt, const void* dot, int Sp, const float* lse, const float* delta, void* dq,
+                                void* dk, void* dv, int B, int H, int S, int head_dim, long long q_bs, long long q_ts,
+                                long long k_bs, long long k_ts, long long v_bs, long long v_ts, long long do_bs,
+                                long long do_ts, long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts,
+                                long long dv_bs, long long dv_ts, const int* qid, const int* kid, const int* qmin,
+                                const int* qmax, const int* kmin, const int* kmax, float scale, const float* rope_table,
+                                int rope_len, const int* rope_pos, int rope_offset, int parts, unsigned int* counters,
+                                long long* prof, int prof_mode, void* stream);
 
 /* tcgen05 / TMEM / TMA forward (attention_tc.cu): q / k / v are strided views ([B][S][H][32], strides in elements);
- * the V tile is read MN-major by the P V MMAs, so no transposed copy is needed; Sq == Sk == S. */
+ * the V tile is read MN-major by the P V MMAs, so no transposed copy is needed; Sq == Sk == S.
+ * counters: 2 caller-owned uint32, zero on entry, zero again on exit (see fk_attn_backward_tc). */
 int fk_attn_forward_tc(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S,
                        int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
                        long long v_ts, long long o_bs, long long o_ts, const int* qid, const int* kid, const int* qmin,
-                       const int* qmax, const int* kmin, const int* kmax, float scale, void* stream);
+                       const int* qmax, const int* kmin, const int* kmax, float scale, unsigned int* counters,
+                       void* stream);
 
 /* Fused residual add + norm on the fp32 residual stream: x_out = x + delta (bf16), y = norm(x_out)
  * (the pair `x = x + branch(...)`; `ln(x)` of models/brainformer.py:243-244).  Backward: dx = norm_backward(g_y) + g_res

@@ -6,7 +6,8 @@ Plain functions over a state_dict with the reference's parameter names, written 
 ``/root/reference``; ``scripts/make_golden.py`` pins it against the unmodified reference modules in the build
 container (fixtures under ``tests/golden``) and ``tests/test_oracle_cpu.py`` re-checks it against them.
 
-Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs import this.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s baseline legs (the CPU arm and the PyTorch-eager-on-GPU
+comparison) import this; the functions follow the device of their inputs.
 """
 from __future__ import annotations
 
@@ -14,11 +15,12 @@ import torch
 import torch.nn.functional as F
 
 
-def rope_cache(dim, seq_len, theta=10000):
-    """build_complex_rope_cache (models/brainformer.py:56-68)."""
+def rope_cache(dim, seq_len, theta=10000, device=None):
+    """build_complex_rope_cache (models/brainformer.py:56-68).  (`device`: the oracle is also run on the GPU in eager
+    PyTorch, as the full-size checker of the parity tests and as bench.py's gpu_eager_baseline.)"""
     freqs = 1.0 / (theta ** (torch.arange(0, dim, 2).float() / dim))
     ang = torch.outer(torch.arange(seq_len), freqs).float()
-    return torch.polar(torch.ones_like(ang), ang)
+    return torch.polar(torch.ones_like(ang), ang).to(device)
 
 
 def apply_rope(x, rope, last=True):
@@ -32,12 +34,12 @@ def apply_rope(x, rope, last=True):
     return torch.view_as_real(xc * rope.unsqueeze(-2)).flatten(3).type_as(x)
 
 
-def block_causal_mask(block_size, tok_per_time):
+def block_causal_mask(block_size, tok_per_time, device=None):
     """build_advanced_causal_mask (models/brainformer.py:93-111), loop form as in the reference."""
     mask = torch.tril(torch.ones(block_size, block_size))
     for i in range(0, block_size, tok_per_time):
         mask[i:i + tok_per_time, i:i + tok_per_time] = 1
-    return mask.bool()
+    return mask.bool().to(device)
 
 
 def self_attention(sd, pre, x, n_heads, attn_mask, rope, rope_last=True):
@@ -97,8 +99,8 @@ def encoder_forward(sd, x, cfg, pre=""):
     n_pat = cfg["window_size"] // cfg["patch_size"]
     h = h + sd[pre + "space_embedding"].repeat(1, n_pat, 1)[:, -n_tok:]
     block_size = n_pat * cfg["n_electrodes"]
-    mask = block_causal_mask(block_size, cfg["n_electrodes"])
-    rope = rope_cache(cfg["head_dim"], block_size, cfg.get("rope_theta", 10000))
+    mask = block_causal_mask(block_size, cfg["n_electrodes"], x.device)
+    rope = rope_cache(cfg["head_dim"], block_size, cfg.get("rope_theta", 10000), x.device)
     for i in range(n_layers(sd, pre + "transformer.h.")):
         h = block(sd, f"{pre}transformer.h.{i}", h, cfg["n_heads"], mask, rope)
     return F.layer_norm(h, (h.shape[-1],), sd[pre + "transformer.ln_f.weight"], sd[pre + "transformer.ln_f.bias"], 1e-5)
@@ -108,18 +110,19 @@ def mae_forward(sd, x, cfg, masked_indices, unmasked_indices):
     """MAE.forward (models/brainformer.py:415-486) with the masking indices supplied by the caller."""
     xp = to_patches(x, cfg["patch_size"])
     b, n_tok, _ = xp.shape
-    rows = torch.arange(b)[:, None]
+    dev = x.device
+    rows = torch.arange(b, device=dev)[:, None]
     n_pat = cfg["window_size"] // cfg["patch_size"]
     block_size = n_pat * cfg["n_electrodes"]
     space = sd["encoder.space_embedding"].repeat(1, n_pat, 1).expand(b, -1, -1)[rows, unmasked_indices]
-    rope = rope_cache(cfg["head_dim"], block_size, cfg.get("rope_theta", 10000)).expand(b, -1, -1)[rows, unmasked_indices]
-    full = block_causal_mask(block_size, cfg["n_electrodes"])
-    sub = full.expand(b, -1, -1)[torch.arange(b)[:, None, None], unmasked_indices[..., None], unmasked_indices[:, None, :]][:, None]
+    rope = rope_cache(cfg["head_dim"], block_size, cfg.get("rope_theta", 10000), dev).expand(b, -1, -1)[rows, unmasked_indices]
+    full = block_causal_mask(block_size, cfg["n_electrodes"], dev)
+    sub = full.expand(b, -1, -1)[torch.arange(b, device=dev)[:, None, None], unmasked_indices[..., None], unmasked_indices[:, None, :]][:, None]
     tok = F.linear(xp[rows, unmasked_indices], sd["encoder.transformer.emb.weight"], sd["encoder.transformer.emb.bias"]) + space
     for i in range(n_layers(sd, "encoder.transformer.h.")):
         tok = block(sd, f"encoder.transformer.h.{i}", tok, cfg["n_heads"], sub, rope)
     tok = F.layer_norm(tok, (tok.shape[-1],), sd["encoder.transformer.ln_f.weight"], sd["encoder.transformer.ln_f.bias"], 1e-5)
-    dec = torch.zeros(b, n_tok, tok.shape[-1])
+    dec = torch.zeros(b, n_tok, tok.shape[-1], device=dev)
     dec[rows, unmasked_indices] = tok
     dec[rows, masked_indices] = sd["mask_token"]
     dec = dec + F.embedding(torch.cat([unmasked_indices, masked_indices], 1), sd["decoder_pos_emb.weight"])
@@ -132,17 +135,18 @@ def mae_forward(sd, x, cfg, masked_indices, unmasked_indices):
 def simple_mae_forward(sd, x, enc_cfg, dec_cfg, masked_indices, unmasked_indices):
     """SimpleMAE.forward (models/simple_mae:338-407) with the masking indices supplied by the caller."""
     b, t, c = x.shape
-    rows = torch.arange(b)[:, None]
+    dev = x.device
+    rows = torch.arange(b, device=dev)[:, None]
     is_padded = (x == 0).all(dim=2)
     attn_mask = ~is_padded.unsqueeze(1) & ~is_padded.unsqueeze(2)
-    sub = attn_mask[torch.arange(b)[:, None, None], unmasked_indices[..., None], unmasked_indices[:, None, :]][:, None]
-    rope = rope_cache(enc_cfg["head_dim"], enc_cfg["block_size"], enc_cfg.get("rope_theta", 10000)).expand(b, -1, -1)[rows, unmasked_indices]
+    sub = attn_mask[torch.arange(b, device=dev)[:, None, None], unmasked_indices[..., None], unmasked_indices[:, None, :]][:, None]
+    rope = rope_cache(enc_cfg["head_dim"], enc_cfg["block_size"], enc_cfg.get("rope_theta", 10000), dev).expand(b, -1, -1)[rows, unmasked_indices]
     tok = F.linear(x[rows, unmasked_indices], sd["encoder.transformer.emb.weight"], sd["encoder.transformer.emb.bias"])
     for i in range(n_layers(sd, "encoder.transformer.h.")):
         tok = block(sd, f"encoder.transformer.h.{i}", tok, enc_cfg["n_heads"], sub, rope, rms=True, rope_last=False)
     tok = F.layer_norm(tok, (tok.shape[-1],), sd["encoder.transformer.ln_f.weight"], sd["encoder.transformer.ln_f.bias"], 1e-5)
     dec_tok = F.linear(tok, sd["decoder.emb.weight"], sd["decoder.emb.bias"])
-    dec = torch.zeros(b, t, dec_tok.shape[-1])
+    dec = torch.zeros(b, t, dec_tok.shape[-1], device=dev)
     dec[rows, unmasked_indices] = dec_tok
     dec[rows, masked_indices] = sd["mask_token"]
     dec = dec + F.embedding(torch.cat([unmasked_indices, masked_indices], 1), sd["decoder_pos_emb.weight"])
@@ -170,7 +174,7 @@ def brainformer_forward(sd, x, enc_cfg, cfg, targets=None):
     ctx = encoder_forward(sd, x, enc_cfg, pre="encoder.")
     b = x.shape[0]
     h = sd["learnable_queries"].expand(b, -1, -1)
-    rope = rope_cache(cfg["head_dim"], cfg["n_output_tokens"], cfg.get("rope_theta", 10000))
+    rope = rope_cache(cfg["head_dim"], cfg["n_output_tokens"], cfg.get("rope_theta", 10000), x.device)
     for i in range(n_layers(sd, "perceiver.h.")):
         p = f"perceiver.h.{i}"
         # CrossBlock.forward (models/brainformer.py:257-268)

@@ -1,5 +1,5 @@
 """Where do the tcgen05 attention-backward CTAs spend their cycles?  Runs fk_attn_backward_tc with the stall-accounting
-instantiation (fk_attn_set_profile_buffer) at the cfg-2 shape and prints per-CTA means.  Diagnosis only."""
+instantiation (fk_attn_backward_tc_profile, selected through ops._BWD_PROFILE) at the cfg-2 shape and prints per-CTA means.  Diagnosis only."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -27,11 +27,11 @@ def main():
             x = qkv.clone().requires_grad_(True)
             out = ops.attention_qkv(x * 1.0, H, None, mask)
             if it == 1:
-                check(lib().fk_attn_set_profile_buffer(ptr(prof), 1), "set")
+                ops._BWD_PROFILE = (prof, 1)
             out.backward(w)
         ops._BWD_PARTS = (2, 4)
         torch.cuda.synchronize()
-        check(lib().fk_attn_set_profile_buffer(None, 1), "unset")
+        ops._BWD_PROFILE = None
         tr = prof[n_cta * 24:].cpu().view(6, 128)
         p = prof[:n_cta * 24].view(n_cta, 24).double().cpu()
         p = p[p[:, 2] > 0]
@@ -64,14 +64,14 @@ def main():
     #      consecutive CTAs on one SM (the kernel runs one CTA per SM)
     for parts, name in ((2, "dK/dV kernel"), (4, "dQ kernel")):
         prof = torch.zeros(n_cta, 24, device=dev, dtype=torch.int64)
-        check(lib().fk_attn_set_profile_buffer(ptr(prof), 2), "set")
+        ops._BWD_PROFILE = (prof, 2)
         ops._BWD_PARTS = (parts,)
         x = qkv.clone().requires_grad_(True)
         out = ops.attention_qkv(x * 1.0, H, None, mask)
         out.backward(w)
         ops._BWD_PARTS = (2, 4)
         torch.cuda.synchronize()
-        check(lib().fk_attn_set_profile_buffer(None, 1), "unset")
+        ops._BWD_PROFILE = None
         p = prof.cpu()
         life, T, g0, g1, sm = p[:, 0].double(), p[:, 2].double(), p[:, 20], p[:, 21], p[:, 22]
         gaps, busy = [], []

@@ -138,8 +138,16 @@ def simple_mae_fixture(sm):
     # the reference's math-path SDPA gives NaN for query rows with no visible key; keep every kept/decoded row
     # non-degenerate by making sure padded bins are masked out of the loss only (the fixture stores what it got)
     loss, _ = quiet(m, x, masking_ratio=0.5)
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    # reconstruction with the same recorded indices (return_preds=True path, models/simple_mae:397-405)
+    m2 = quiet(sm.SimpleMAE, EC(), MC())
+    m2.load_state_dict(m.state_dict())
+    m2.get_masking_indices = lambda r, xx: (rec["masked"], rec["unmasked"])
+    with torch.no_grad():
+        _, recon, binary = quiet(m2, x, masking_ratio=0.5, return_preds=True)
     return dict(enc_config=EC().__dict__, mae_config=MC().__dict__, state={k: v.clone() for k, v in m.state_dict().items()}, x=x,
-                loss=loss.detach(), masked=rec["masked"], unmasked=rec["unmasked"])
+                loss=loss.detach(), masked=rec["masked"], unmasked=rec["unmasked"], grads=grads, recon=recon, binary=binary)
 
 
 def main():

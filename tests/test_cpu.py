@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     for name in protos:
         assert hasattr(L, name), f"{name} declared in include/fk_b200.h but not exported"
     L2 = _lib.lib()
-    assert L2.fk_abi_version() == 1 and L2.fk_target_sm() == 100
+    assert L2.fk_abi_version() == 2 and L2.fk_target_sm() == 100
     assert L2.fk_last_error() is not None
 
 

@@ -64,8 +64,12 @@ def test_brainformer_oracle_matches_reference():
 def test_simple_mae_oracle_matches_reference():
     from oracle import brainformer_ref as o
     g = load("simple_mae_small.pt")
-    loss, _ = o.simple_mae_forward(g["state"], g["x"], g["enc_config"], g["mae_config"], g["masked"], g["unmasked"])
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state"].items()}
+    loss, _ = o.simple_mae_forward(sd, g["x"], g["enc_config"], g["mae_config"], g["masked"], g["unmasked"])
     assert torch.allclose(loss, g["loss"], rtol=1e-5), (loss, g["loss"])
+    loss.backward()
+    for n, ref in g["grads"].items():
+        assert torch.allclose(sd[n].grad, ref, rtol=1e-4, atol=1e-6), n
 
 
 @pytest.mark.parametrize("cosine", [False, True])
@@ -133,3 +137,60 @@ def test_vq_oracle_two_rank_allreduce_equals_single_rank():
     vq(X[None])
     for k, v in vq.state_dict().items():
         assert torch.allclose(got[k], v, rtol=1e-5, atol=1e-6), k
+
+
+def _encodec_lineage_codebook():
+    """EuclideanCodebook of the encodec lineage as shipped inside the installed vllm wheel
+    (vllm/model_executor/models/mimo_audio.py, "Vector quantization (from MiMo-Audio-Tokenizer)"): NOT the reference's
+    dependency, but an independent implementation of the same published algorithm (EMA cluster sizes, EMA embedding
+    sums, Laplace smoothing, embed = embed_avg / smoothed size) -- SURVEY.md section 8c names it as the sibling-lineage
+    cross-check for the unpinned quantiser oracle.  Only the self-contained VQ section of the file is executed."""
+    import importlib.util
+    import typing as tp
+    import torch.distributed as dist
+    import torch.nn as nn
+    import torch.nn.functional as F
+    einops = pytest.importorskip("einops")
+    spec = importlib.util.find_spec("vllm")
+    if spec is None or not spec.submodule_search_locations:
+        pytest.skip("vllm is not installed")
+    path = os.path.join(list(spec.submodule_search_locations)[0], "model_executor", "models", "mimo_audio.py")
+    if not os.path.exists(path):
+        pytest.skip("this vllm build has no mimo_audio.py")
+    src = open(path).read()
+    try:
+        a = src.index("def _vq_default")
+        a_end = src.index("\nclass ", a)
+        b = src.index("class EuclideanCodebook")
+        b_end = src.index("\nclass ", b + 10)
+    except ValueError:
+        pytest.skip("mimo_audio.py no longer has the expected VQ section")
+    ns = dict(torch=torch, nn=nn, F=F, dist=dist, tp=tp, rearrange=einops.rearrange, repeat=einops.repeat)
+    exec(compile(src[a:a_end] + "\n" + src[b:b_end], path, "exec"), ns)
+    return ns["EuclideanCodebook"]
+
+
+def test_vq_oracle_against_encodec_lineage_codebook():
+    """Second anchor for the unpinned oracle: three training steps of the oracle's Euclidean codebook and of the
+    encodec-lineage one from the same state on the same batches give the same indices, quantised rows and EMA state
+    (threshold 0: the two lineages differ in WHEN dead codes are re-drawn, not in the EMA arithmetic)."""
+    from oracle.vector_quantize_ref import VectorQuantizeRef
+    Codebook = _encodec_lineage_codebook()
+    K, D, N = 48, 16, 400
+    g = torch.Generator().manual_seed(0)
+    C = torch.randn(K, D, generator=g)
+    ref = VectorQuantizeRef(dim=D, codebook_size=K, commitment_weight=0.25, decay=0.8, eps=1e-5, threshold_ema_dead_code=0).train()
+    ref._codebook.embed.copy_(C[None]); ref._codebook.embed_avg.copy_(C[None]); ref._codebook.cluster_size.fill_(1.0)
+    ref._codebook.initted.fill_(1.0)
+    other = Codebook(dim=D, codebook_size=K, kmeans_init=False, decay=0.8, epsilon=1e-5, threshold_ema_dead_code=0).train()
+    other.embed.copy_(C); other.embed_avg.copy_(C); other.cluster_size.fill_(1.0)
+    for step in range(3):
+        x = C[torch.randint(0, K, (N,), generator=g)] + 0.4 * torch.randn(N, D, generator=g)
+        q_ref, i_ref, _ = ref(x[None])
+        q_o, i_o = other(x)
+        assert torch.equal(i_ref.view(-1), i_o.view(-1)), step
+        # (the oracle returns the straight-through value x + (q - x).detach(): the same numbers up to one rounding)
+        assert torch.allclose(q_ref.view(N, D), q_o, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(ref._codebook.cluster_size[0], other.cluster_size, rtol=1e-5, atol=1e-6), step
+        assert torch.allclose(ref._codebook.embed_avg[0], other.embed_avg, rtol=1e-5, atol=1e-5), step
+        assert torch.allclose(ref._codebook.embed[0], other.embed, rtol=1e-4, atol=1e-5), step

@@ -83,7 +83,10 @@ def test_search_marks_unowned_slots(N, K, D, ctas):
 @pytest.mark.parametrize("N,K,D,kind", [(4096, 512, 64, "clustered"), (4096, 512, 64, "random"),
                                         (16384, 8192, 256, "clustered"), (8192, 8192, 256, "random"),
                                         (1000, 333, 64, "random"), (5, 7, 64, "random"),
-                                        (4096, 16384, 256, "random"), (2048, 65536, 256, "clustered")])   # cfg-5 sweep ends
+                                        (4096, 16384, 256, "random"), (2048, 65536, 256, "clustered"),    # cfg-5 sweep ends
+                                        (16384, 8192, 256, "random"),                                      # cfg 4 size, Gaussian
+                                        (4096, 1024, 256, "random"), (4096, 2048, 256, "random"),          # remaining sweep K
+                                        (4096, 4096, 256, "random"), (2048, 32768, 256, "random")])
 def test_eval_forward_matches_oracle(N, K, D, kind, cosine):
     fvq, ovq = _mods()
     if kind == "clustered":
@@ -136,8 +139,17 @@ def test_train_step_matches_oracle(B, T, K, D, cosine):
         Xs = torch.nn.functional.normalize(x.view(-1, D), dim=-1) if cosine else x.view(-1, D)
         agree, worst = index_agreement(i, i_ref, Xs, ref._codebook.embed[0], cosine)
         assert agree == 1.0 or (agree >= 0.999 and worst < 1e-3), (step, agree, worst)
+        same = (i.cpu() == i_ref).reshape(-1)
         if agree < 1.0:
-            pytest.skip("a near-tie flipped; EMA state legitimately diverges from here")
+            # a documented near-tie flipped: this step is compared on the agreeing rows (the loss, a mean over all rows,
+            # moves by at most the flipped rows' share), and the oracle's state is re-based on ours so that the
+            # remaining steps are compared exactly again instead of being skipped
+            n_flip = int((~same).sum())
+            assert torch.allclose(l.cpu(), l_ref, rtol=RTOL + 2.0 * n_flip / same.numel(), atol=1e-7), (step, l, l_ref)
+            assert torch.allclose(q.detach().cpu().reshape(-1, D)[same], q_ref.detach().reshape(-1, D)[same], rtol=RTOL, atol=1e-6)
+            assert torch.allclose(xm.grad.cpu().reshape(-1, D)[same], xr.grad.reshape(-1, D)[same], rtol=RTOL, atol=1e-5)
+            ref.load_state_dict({k: v.cpu() for k, v in mine.state_dict().items()})
+            continue
         assert torch.allclose(l.cpu(), l_ref, rtol=RTOL, atol=1e-7), (step, l, l_ref)
         assert torch.allclose(q.detach().cpu(), q_ref.detach(), rtol=RTOL, atol=1e-6)
         assert torch.allclose(xm.grad.cpu(), xr.grad, rtol=RTOL, atol=1e-5), (xm.grad.cpu() - xr.grad).abs().max()
@@ -260,3 +272,74 @@ def test_full_size_properties_cfg4():
     assert (i2.view(-1) == torch.arange(K, device="cuda")).float().mean() >= 0.999
     assert torch.equal(q2.view(K, D)[i2.view(-1) == torch.arange(K, device="cuda")],
                        Cd[i2.view(-1) == torch.arange(K, device="cuda")])
+
+
+def test_ema_stats_deterministic_and_exact():
+    """K5 as a segmented sum in ascending row order: bit-identical from run to run (the fp32-atomic version was not) and
+    equal to an fp64 index_add; covers short segments (<= 32 rows, in-warp rank sort), long ones (a hot code) and
+    empty codes."""
+    fvq, _ = _mods()
+    N, K, D = 16384, 512, 256
+    g = torch.Generator().manual_seed(5)
+    xn = torch.randn(N, D, generator=g).cuda()
+    ind = torch.randint(0, K, (N,), generator=g)
+    ind[:3000] = 7                       # one hot code (long segment)
+    ind[ind == 11] = 12                  # one empty code
+    ind = ind.cuda()
+    first = fvq.ema_stats(xn, ind, K)
+    for _ in range(3):
+        assert torch.equal(fvq.ema_stats(xn, ind, K), first)
+    ref = torch.zeros(K, D, dtype=torch.float64, device="cuda").index_add_(0, ind, xn.double())
+    assert torch.allclose(first[:K * D].view(K, D).double(), ref, rtol=1e-5, atol=1e-4)
+    assert torch.equal(first[K * D:], torch.bincount(ind, minlength=K).float())
+    assert first[K * D + 11] == 0 and (first[11 * D:12 * D] == 0).all()
+
+
+@pytest.mark.parametrize("cosine", [False, True])
+def test_side_stream_ema_equals_in_stream(cosine):
+    """The EMA all-reduce + finalize on a side stream (overlap_ema) leaves exactly the state of the in-stream order, step
+    after step (the next search waits on the event), and state_dict() waits for a pending update."""
+    fvq, _ = _mods()
+    B, T, K, D = 4, 128, 256, 64
+    X, C = make_vq_problem(B * T, K, D, seed=3, cosine=cosine, noise=0.5)
+    mods = []
+    for mode in (False, "always"):
+        m = fvq.VectorQuantize(dim=D, codebook_size=K, commitment_weight=0.25, use_cosine_sim=cosine,
+                               threshold_ema_dead_code=2).cuda().train()
+        m._codebook.embed.copy_(C[None].cuda()); m._codebook.embed_avg.copy_(C[None].cuda()); m._codebook.cluster_size.fill_(1.0)
+        m._mark_dirty(); m._kmeans_initted_host = True
+        m.overlap_ema = mode
+        m.sample_rows_override = torch.arange(B * T)
+        mods.append(m)
+    g = torch.Generator().manual_seed(1)
+    for step in range(4):
+        x = (X + 0.05 * torch.randn(X.shape, generator=g)).view(B, T, D).cuda()
+        outs = [m(x) for m in mods]
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+        sd0, sd1 = mods[0].state_dict(), mods[1].state_dict()
+        for k in sd0:
+            assert torch.equal(sd0[k], sd1[k]), (step, k)
+
+
+def test_module_pickles_and_residual_vq():
+    """torch.save(model) works (no lambda hooks); ResidualVQ (imported by models/vq_brain.py:6) quantises residuals."""
+    import io
+    fvq, ovq = _mods()
+    m = fvq.VectorQuantize(dim=64, codebook_size=32).cuda()
+    torch.save(m, io.BytesIO())
+    torch.manual_seed(0)
+    rvq = fvq.ResidualVQ(dim=64, num_quantizers=3, codebook_size=64, kmeans_init=False, commitment_weight=0.25).cuda().eval()
+    x = torch.randn(2, 50, 64).cuda()
+    q, ind, loss = rvq(x)
+    assert q.shape == x.shape and ind.shape == (2, 50, 3) and loss.shape == (1, 3)
+    # oracle: the same greedy residual loop over the fp32 reference quantiser with the same codebooks
+    resid, acc = x.cpu(), torch.zeros_like(x.cpu())
+    for li, layer in enumerate(rvq.layers):
+        ref = ovq.VectorQuantizeRef(dim=64, codebook_size=64, commitment_weight=0.25).eval()
+        ref._codebook.embed.copy_(layer._codebook.embed.cpu())
+        qr, ir, _ = ref(resid)
+        assert (ir == ind[..., li].cpu()).float().mean() >= 0.999
+        resid, acc = resid - qr, acc + qr
+    assert torch.allclose(q.cpu(), acc, rtol=RTOL, atol=1e-4)
+    # residual norm shrinks layer by layer
+    assert (x - q).norm() < x.norm()
