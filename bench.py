@@ -1,15 +1,16 @@
 #!/usr/bin/env python
-"""Benchmark of the neural-encoder training step (BASELINE.json metric: trials/sec of the VQ + Brainformer
-train step; VQ-search fraction of the bf16 tensor-core peak).
+"""Benchmark of the neural-encoder training step (BASELINE.json metric: trials/sec of the VQ + Brainformer train step;
+VQ-search fraction of the bf16 tensor-core peak).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W                      # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W     # the reference's CPU path (oracle port)
+    python bench.py --workload cfg3-mae | cfg3-simple-mae | cfg1-vqvae | cfg2-encoder   # the other BASELINE configs
+    python bench.py --scaling strong --gpus N                          # global batch 128 split over N GPUs (split_batches=True)
 
-Workload "cfg4-joint" (per GPU): 128 synthetic trials x[512 bins, 512 ch] ->
-SoundStream(C=256, D=256, K=8192, Euclidean) on all 512 channels  +  BrainFormer (Encoder window 512, 256
-electrodes, patch 32 -> 4096 tokens/trial, dim 512, 4 layers, 16 heads x 32, hidden 2048, + perceiver) on the
-first 256 channels; loss = sum of both; one backward; value-clip(1.0); fused AdamW.  Weak scaling: 128 trials
-per GPU.  One step = one pass over one batch.
+Default workload "cfg4-joint" (per GPU): 128 synthetic trials x[512 bins, 512 ch] ->
+SoundStream(C=256, D=256, K=8192, Euclidean) on all 512 channels  +  BrainFormer (Encoder window 512, 256 electrodes,
+patch 32 -> 4096 tokens/trial, dim 512, 4 layers, 16 heads x 32, hidden 2048, + perceiver) on the first 256 channels;
+loss = sum of both; one backward; value-clip(1.0); fused AdamW.  One step = one pass over one batch.
 """
 from __future__ import annotations
 
@@ -34,24 +35,41 @@ TRIALS_PER_GPU = 128
 T_BINS, N_CH = 512, 512
 VQ_K, VQ_D, VQ_C = 8192, 256, 256
 CPU_SAMPLE_TRIALS = 2
-WORKLOAD = ("cfg4-joint: SoundStream(C=256,D=256,K=8192,euclid) on 512 ch + BrainFormer(Encoder window 512, "
-            "256 electrodes, patch 32 -> 4096 tokens/trial, dim 512, 4 layers, 16x32 heads, hidden 2048; "
-            "perceiver 32 tokens) on 256 ch; AdamW + value clip")
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-# (attention rows: the capture in profiles/r01_attention_tc_ncu_full.txt is a 16-trial launch; trials are independent,
-#  so a B-trial launch moves B/16 times those bytes)
+METRIC = "trials/sec VQ+Brainformer train step"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/);
+# attention rows: 16-trial launches (trials are independent, so a B-trial launch moves B/16 times those bytes)
 NCU_TRAFFIC = {"vq_search": 12660224}
 NCU_TRAFFIC_PER_16_TRIALS = {"attn_fwd": 202000896 + 54899712, "attn_bwd_dkv": 277223424 + 112426240,
                              "attn_bwd_dq": 277200640 + 58217984}
 
+ENC_CFG = dict(window_size=512, n_electrodes=256, patch_size=32, dim=512, n_layers=4, head_dim=32, hidden_dim=2048,
+               n_heads=16, n_kv_heads=16, n_dec_layers=4, decoder_dim=512)
+PER_CFG = dict(n_output_tokens=32, output_dim=768, dim=512, n_layers=2, head_dim=16, hidden_dim=512, n_heads=4, n_kv_heads=4)
+SIMPLE_ENC_CFG = dict(block_size=512, patch_size=256, n_layers=4, dim=512, hidden_dim=2048, head_dim=32, n_heads=16,
+                      n_kv_heads=16, rope_theta=10000)
+SIMPLE_MAE_CFG = dict(n_layers=2, dim=512, hidden_dim=2048, head_dim=32, n_heads=16, n_kv_heads=16, rope_theta=10000)
+
+WORKLOADS = {
+    "cfg4-joint": ("cfg4-joint: SoundStream(C=256,D=256,K=8192,euclid) on 512 ch + BrainFormer(Encoder window 512, "
+                   "256 electrodes, patch 32 -> 4096 tokens/trial, dim 512, 4 layers, 16x32 heads, hidden 2048; "
+                   "perceiver 32 tokens) on 256 ch; AdamW + value clip"),
+    "cfg2-encoder": ("cfg2-encoder: BrainFormer (Encoder window 512, 256 electrodes, patch 32 -> 4096 tokens/trial, dim 512, "
+                     "4 layers, 16x32 heads, hidden 2048; perceiver 32 tokens) on 256 ch; AdamW + value clip"),
+    "cfg3-mae": ("cfg3-mae: brainformer.MAE, 75 % token masking (1024 of 4096 tokens kept per trial, encoder 4 layers on the "
+                 "kept tokens with gathered labels + rope, decoder 4 layers on all 4096), dim 512, 16x32 heads, hidden 2048; "
+                 "AdamW + value clip"),
+    "cfg3-simple-mae": ("cfg3-simple-mae: SimpleMAE on x[B,512,256] (one token per time bin), encoder 4 layers dim 512 "
+                        "hidden 2048 RMSNorm, decoder 2 layers, 75 % masking, padding masks; AdamW + value clip"),
+    "cfg1-vqvae": ("cfg1-vqvae: SoundStream(C=256, D=64, K=512, cosine) VQ-VAE step on 32 trials x 512 ch x 512 bins "
+                   "(the reference's CPU-runnable configuration, here on the GPU); AdamW + value clip"),
+}
+DEFAULT_TRIALS = {"cfg4-joint": 128, "cfg2-encoder": 128, "cfg3-mae": 128, "cfg3-simple-mae": 128, "cfg1-vqvae": 32}
+
 
 def model_configs():
     from frankenstein_b200.brainformer import Config, MAEConfig
-    enc = MAEConfig(window_size=512, n_electrodes=256, patch_size=32, dim=512, n_layers=4, head_dim=32, hidden_dim=2048,
-                    n_heads=16, n_kv_heads=16, n_dec_layers=4, decoder_dim=512)
-    per = Config(encoder=enc, n_output_tokens=32, output_dim=768, dim=512, n_layers=2, head_dim=16, hidden_dim=512,
-                 n_heads=4, n_kv_heads=4)
-    return enc, per
+    enc = MAEConfig(**ENC_CFG)
+    return enc, Config(encoder=enc, **PER_CFG)
 
 
 class Joint(nn.Module):
@@ -69,6 +87,51 @@ class Joint(nn.Module):
         l_vq, _ = self.vqvae(x)
         l_bf, _ = self.brainformer(x[..., :256].contiguous(), targets)
         return l_vq + l_bf
+
+
+class _EncoderOnly(nn.Module):
+    def __init__(self):
+        super().__init__()
+        from frankenstein_b200.brainformer import BrainFormer
+        self.brainformer = BrainFormer(model_configs()[1])
+
+    def forward(self, x, targets):
+        return self.brainformer(x[..., :256].contiguous(), targets)[0]
+
+
+class _MAEOnly(nn.Module):
+    def __init__(self):
+        super().__init__()
+        from frankenstein_b200.brainformer import MAE
+        self.mae = MAE(model_configs()[0])
+
+    def forward(self, x, targets):
+        return self.mae(x[..., :256].contiguous())[0]
+
+
+class _SimpleMAEOnly(nn.Module):
+    def __init__(self):
+        super().__init__()
+        from frankenstein_b200 import simple_mae as sm
+        self.mae = sm.SimpleMAE(sm.SimpleEncoderConfig(**SIMPLE_ENC_CFG), sm.SimpleMAEConfig(**SIMPLE_MAE_CFG))
+
+    def forward(self, x, targets):
+        return self.mae(x[..., :256].contiguous())[0]
+
+
+class _VQVAEOnly(nn.Module):
+    def __init__(self):
+        super().__init__()
+        from frankenstein_b200.vq_brain import SoundStream
+        self.vqvae = SoundStream(C=256, D=64, codebook_size=512, n_electrodes=N_CH, use_cosine_sim=True)
+
+    def forward(self, x, targets):
+        return self.vqvae(x)[0].sum()
+
+
+def build_model(workload):
+    return {"cfg4-joint": Joint, "cfg2-encoder": _EncoderOnly, "cfg3-mae": _MAEOnly, "cfg3-simple-mae": _SimpleMAEOnly,
+            "cfg1-vqvae": _VQVAEOnly}[workload]()
 
 
 def synth_batch(n, seed):
@@ -134,46 +197,249 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the reference's own CPU path restated in oracle/ (the reference tree is not on the GPU box)
+# baselines: the reference's own path restated in oracle/ (the reference tree is not on the GPU box), timed on the host
+# cores (cpu_baseline / --impl reference) and, as the per-kernel competitor, in eager PyTorch on the same B200
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, trials=CPU_SAMPLE_TRIALS):
-    from frankenstein_b200.brainformer import BrainFormer
-    from frankenstein_b200.vq_brain import SoundStream
-    from oracle import brainformer_ref
-    from oracle.soundstream_ref import SoundStreamRef
+class _OracleStep:
+    """zero_grad -> fwd -> bwd -> value-clip -> AdamW on the oracle restatement of a workload, on `device`."""
+
+    def __init__(self, workload, device, autocast_dtype=None):
+        from frankenstein_b200.brainformer import MAE, BrainFormer
+        from frankenstein_b200 import simple_mae as sm
+        from frankenstein_b200.vq_brain import SoundStream
+        from oracle import brainformer_ref
+        from oracle.soundstream_ref import SoundStreamRef
+        self.ref, self.workload, self.device, self.autocast = brainformer_ref, workload, device, autocast_dtype
+        torch.manual_seed(0)
+        enc, per = model_configs()
+        self.ss = self.bf_sd = self.mae_sd = self.smae_sd = None
+        params = []
+        if workload in ("cfg4-joint", "cfg1-vqvae"):
+            kw = (dict(C=VQ_C, D=VQ_D, codebook_size=VQ_K, use_cosine_sim=False) if workload == "cfg4-joint"
+                  else dict(C=256, D=64, codebook_size=512, use_cosine_sim=True))
+            sd = {k: v.to(device) for k, v in SoundStream(n_electrodes=N_CH, **kw).state_dict().items()}
+            self.ss = SoundStreamRef(sd, kw["D"], kw["codebook_size"], use_cosine_sim=kw["use_cosine_sim"], training=True)
+            self.ss.vq.to(device)
+            params += self.ss.parameters()
+
+        def grad_sd(module):
+            return {k: v.detach().clone().to(device).requires_grad_(v.is_floating_point() and "attn_mask" not in k)
+                    for k, v in module.state_dict().items()}
+        if workload in ("cfg4-joint", "cfg2-encoder"):
+            self.bf_sd = grad_sd(BrainFormer(per))
+            params += [v for v in self.bf_sd.values() if v.requires_grad]
+        if workload == "cfg3-mae":
+            self.mae_sd = grad_sd(MAE(enc))
+            params += [v for v in self.mae_sd.values() if v.requires_grad]
+        if workload == "cfg3-simple-mae":
+            self.smae_sd = grad_sd(sm.SimpleMAE(sm.SimpleEncoderConfig(**SIMPLE_ENC_CFG), sm.SimpleMAEConfig(**SIMPLE_MAE_CFG)))
+            params += [v for v in self.smae_sd.values() if v.requires_grad]
+        self.params = params
+        self.opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
+
+    def _indices(self, b, n):
+        order = torch.rand(b, n, device=self.device).argsort(dim=-1)
+        k = int(0.75 * n)
+        return torch.sort(order[:, :k], dim=1)[0], torch.sort(order[:, k:], dim=1)[0]
+
+    def loss(self, x, t):
+        enc_cfg = dict(ENC_CFG)
+        loss = 0.0
+        if self.ss is not None:
+            loss = loss + self.ss(x)[0].sum()
+        if self.bf_sd is not None:
+            loss = loss + self.ref.brainformer_forward(self.bf_sd, x[..., :256].contiguous(), enc_cfg, dict(PER_CFG), t)[0]
+        if self.mae_sd is not None:
+            m, u = self._indices(x.shape[0], 4096)
+            loss = loss + self.ref.mae_forward(self.mae_sd, x[..., :256].contiguous(), enc_cfg, m, u)[0]
+        if self.smae_sd is not None:
+            m, u = self._indices(x.shape[0], T_BINS)
+            loss = loss + self.ref.simple_mae_forward(self.smae_sd, x[..., :256].contiguous(), SIMPLE_ENC_CFG, SIMPLE_MAE_CFG, m, u)[0]
+        return loss
+
+    def step(self, x, t):
+        self.opt.zero_grad(set_to_none=True)
+        if self.autocast is not None:
+            with torch.autocast(self.device.type, dtype=self.autocast):
+                loss = self.loss(x, t)
+        else:
+            loss = self.loss(x, t)
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(self.params, 1.0)
+        self.opt.step()
+        return loss
+
+
+def cpu_reference_run(workload, steps, warmup, trials):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    enc, per = model_configs()
-    ss_sd = SoundStream(C=VQ_C, D=VQ_D, codebook_size=VQ_K, n_electrodes=N_CH, use_cosine_sim=False).state_dict()
-    bf_sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "attn_mask" not in k)
-             for k, v in BrainFormer(per).state_dict().items()}
-    ss = SoundStreamRef(ss_sd, VQ_D, VQ_K, use_cosine_sim=False, training=True)
-    enc_cfg = dict(window_size=512, n_electrodes=256, patch_size=32, head_dim=32, n_heads=16)
-    per_cfg = dict(head_dim=16, n_output_tokens=32, n_heads=4)
-    params = ss.parameters() + [v for v in bf_sd.values() if v.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
+    runner = _OracleStep(workload, torch.device("cpu"))
     x, t = synth_batch(trials, 99)
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        l_vq, _ = ss(x)
-        l_bf, _ = brainformer_ref.brainformer_forward(bf_sd, x[..., :256].contiguous(), enc_cfg, per_cfg, t)
-        loss = l_vq + l_bf
-        loss.backward()
-        torch.nn.utils.clip_grad_value_(params, 1.0)
-        opt.step()
-        return float(loss.detach())
-
     for _ in range(warmup):
-        step()
+        runner.step(x, t)
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        runner.step(x, t)
     dt = time.perf_counter() - t0
     return {"value": trials * steps / dt, "unit": "trials/s", "cores": cores, "kind": "port",
             "sample": f"{steps} timed steps of {trials} trial(s) after {warmup} warm-up, fp32, torch {torch.__version__} "
-                      f"on {cores} host threads, oracle/ restatement of models/vq_brain.py + models/brainformer.py"}, dt / steps * 1e3
+                      f"on {cores} host threads, oracle/ restatement of the reference modules ({workload})"}, dt / steps * 1e3
+
+
+def gpu_eager_run(workload, dev, trials, steps=3, warmup=2):
+    """The same oracle restatement in eager PyTorch on the B200 (library kernels: cuBLAS / cuDNN / SDPA with the dense
+    bool masks the reference builds): the per-kernel competitor SURVEY section 2a names.  fp32 and bf16 autocast."""
+    out = {}
+    x, t = synth_batch(trials, 77)
+    x, t = x.to(dev), t.to(dev)
+    for name, dt in (("bf16_autocast", torch.bfloat16), ("fp32", None)):
+        try:
+            runner = _OracleStep(workload, dev, dt)
+            for _ in range(warmup):
+                runner.step(x, t)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                runner.step(x, t)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": trials / (ms * 1e-3), "unit": "trials/s", "ms_per_step": ms, "trials_per_step": trials}
+            del runner
+        except Exception as e:  # informational; an OOM of the eager path must not lose the line
+            out[name] = {"value": None, "error": f"{type(e).__name__}: {str(e)[:200]}"}
+        torch.cuda.empty_cache()
+    out["what"] = ("oracle/ restatement of the reference modules in eager PyTorch on the same GPU (cuBLAS, cuDNN, "
+                   "mem-efficient SDPA with dense [S,S] bool masks, one-hot VQ GEMMs); same optimizer step")
+    return out
+
+
+def eager_op_table(dev):
+    """Per-op comparison at the cfg-4 shapes: library (PyTorch eager) kernel sequence vs ours, ms each, CUDA events."""
+    import torch.nn.functional as F
+    from frankenstein_b200 import ops
+    from frankenstein_b200 import vector_quantize as fvq
+    from frankenstein_b200 import gemm
+
+    def time_ms(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    g = torch.Generator().manual_seed(0)
+    rows = {}
+    # --- VQ: cdist + argmax + one-hot GEMMs (what the reference's dependency launches) vs search + finish + ema stats ---
+    N, K, D = 16384, VQ_K, VQ_D
+    X = torch.randn(N, D, generator=g).to(dev)
+    C = torch.randn(K, D, generator=g).to(dev)
+
+    def vq_eager():
+        d = -torch.cdist(X[None], C[None])[0]
+        ind = d.argmax(-1)
+        oh = F.one_hot(ind, K).float()
+        q = oh @ C
+        return q, oh.sum(0), X.t() @ oh
+
+    xn, xb, _ = fvq.prepare_input(X, False)
+    cb, c2 = fvq.prepare_codebook(C, False)
+
+    def vq_ours():
+        cv, ci = fvq.search(xb, cb, c2, K, False)
+        ind, q, _ = fvq.finish(xn, C, cv, ci, False, True, 0.25)
+        return fvq.ema_stats(xn, ind, K)
+
+    rows["vq search+gather+ema_stats (N=16384,K=8192,D=256)"] = {"eager_ms": time_ms(vq_eager), "ours_ms": time_ms(vq_ours)}
+    # --- attention fwd+bwd, 16 trials: SDPA with the dense block-causal bool mask vs label-mask tcgen05 kernels ---
+    B, S, H = 16, 4096, 16
+    qkv = torch.randn(B, S, 3 * H * 32, generator=g).to(dev).to(torch.bfloat16)
+    dense = (torch.arange(S, device=dev) // 256)[None, :] <= (torch.arange(S, device=dev) // 256)[:, None]
+    mask = ops.LabelMask.block_causal(B, S, 256, dev)
+
+    def attn_eager():
+        x = qkv.clone().requires_grad_(True)
+        q, k, v = (t.transpose(1, 2) for t in x.view(B, S, 3, H, 32).unbind(2))
+        F.scaled_dot_product_attention(q, k, v, attn_mask=dense).sum().backward()
+
+    def attn_ours():
+        x = qkv.clone().requires_grad_(True)
+        ops.attention_qkv(x * 1.0, H, None, mask).sum().backward()
+
+    rows["attention fwd+bwd (16 trials, S=4096, 16x32 heads, block-causal)"] = {"eager_ms": time_ms(attn_eager, 3, 1),
+                                                                                  "ours_ms": time_ms(attn_ours, 3, 1)}
+    # --- SwiGLU MLP fwd+bwd on 16 trials: three F.linear + silu*mul vs fused-epilogue GEMMs ---
+    M = B * S
+    x0 = torch.randn(M, 512, generator=g).to(dev).to(torch.bfloat16)
+    w1, w3 = (torch.randn(2048, 512, generator=g).to(dev) * 0.04 for _ in range(2))
+    w2 = torch.randn(512, 2048, generator=g).to(dev) * 0.02
+    for w in (w1, w3, w2):
+        w.requires_grad_(True)
+
+    def mlp_eager():
+        x = x0.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            F.linear(F.silu(F.linear(x, w1)) * F.linear(x, w3), w2).sum().backward()
+
+    def mlp_ours():
+        x = x0.clone().requires_grad_(True)
+        gemm.swiglu_mlp(x, w1, w3, w2).sum().backward()
+
+    rows["SwiGLU MLP fwd+bwd (65536 x 512 -> 2048 -> 512)"] = {"eager_ms": time_ms(mlp_eager), "ours_ms": time_ms(mlp_ours)}
+    # --- residual add + LayerNorm fwd+bwd ---
+    xr = torch.randn(M, 512, generator=g).to(dev)
+    dl = torch.randn(M, 512, generator=g).to(dev).to(torch.bfloat16)
+    lw, lb = torch.ones(512, device=dev, requires_grad=True), torch.zeros(512, device=dev, requires_grad=True)
+
+    def ln_eager():
+        a, b = xr.clone().requires_grad_(True), dl.clone().requires_grad_(True)
+        h = a + b.float()
+        (F.layer_norm(h, (512,), lw, lb).to(torch.bfloat16).sum() + h.sum()).backward()
+
+    def ln_ours():
+        a, b = xr.clone().requires_grad_(True), dl.clone().requires_grad_(True)
+        h, y = ops.add_layer_norm(a, b, lw, lb)
+        (y.sum() + h.sum()).backward()
+
+    rows["residual add + LayerNorm fwd+bwd (65536 x 512)"] = {"eager_ms": time_ms(ln_eager), "ours_ms": time_ms(ln_ours)}
+    for r in rows.values():
+        r["speedup"] = r["eager_ms"] / r["ours_ms"]
+    return rows
+
+
+def vq_search_sweep(dev, peak_burst):
+    """BASELINE config 5: codebook-size sweep 512 -> 65536 (N = 16384, D = 256, Euclidean), search kernel alone."""
+    from frankenstein_b200 import vector_quantize as fvq
+    g = torch.Generator().manual_seed(0)
+    N, D = 16384, 256
+    X = torch.randn(N, D, generator=g).to(dev)
+    _, xb, _ = fvq.prepare_input(X, False)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    out = []
+    for K in (512, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
+        C = torch.randn(K, D, generator=g).to(dev)
+        cb, c2 = fvq.prepare_codebook(C, False)
+        for _ in range(3):
+            fvq.search(xb, cb, c2, K, False)
+        ms = []
+        for _ in range(5):
+            flush.zero_()                                    # L2 flush between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fvq.search(xb, cb, c2, K, False)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms.append(e0.elapsed_time(e1))
+        t = statistics.median(ms)
+        tf = 2.0 * N * K * D / (t * 1e-3) / 1e12
+        out.append({"K": K, "us": t * 1e3, "tflops": tf, "frac_of_burst_peak": tf / peak_burst})
+    return out
 
 
 def run_reference(args):
@@ -181,12 +447,15 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    base, ms = cpu_reference_run(steps, warmup)
-    line = {"impl": "reference", "metric": "trials/sec VQ+Brainformer train step", "value": base["value"], "unit": "trials/s",
+    trials = 32 if args.workload == "cfg1-vqvae" else (8 if args.workload == "cfg3-simple-mae" else CPU_SAMPLE_TRIALS)
+    base, ms = cpu_reference_run(args.workload, steps, warmup, trials)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "trials/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "trials_per_gpu": TRIALS_PER_GPU, "bins": T_BINS,
-                       "sample": f"bounded CPU sample of the same step: {CPU_SAMPLE_TRIALS} trials per timed step, scaled to trials/s"},
+            "config": {"workload": WORKLOADS[args.workload], "trials_per_gpu": trials, "trials_per_gpu_of_the_gpu_arm": DEFAULT_TRIALS[args.workload],
+                       "bins": T_BINS,
+                       "sample": f"bounded CPU sample of the same step: {trials} trials per timed step (the GPU arm steps "
+                                 f"{DEFAULT_TRIALS[args.workload]} per GPU), throughput in trials/s"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -195,14 +464,40 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+KERNEL_NAMES = {
+    "vq_search": "fk::vq_search_kernel (tcgen05/TMEM/TMA nearest-codeword search)",
+    "attn_fwd": "fk::attn_fwd_tc_kernel (label-mask flash attention forward, tcgen05/TMEM/TMA)",
+    "attn_bwd_dkv": "fk::attn_bwd_tc_kernel<DKV> (label-mask flash attention dK/dV, tcgen05/TMEM/TMA)",
+    "attn_bwd_dq": "fk::attn_bwd_tc_kernel<DQ> (label-mask flash attention dQ, tcgen05/TMEM/TMA)",
+    "gemm_qkv_rope": "fk::gemm_res_kernel<ROPE> (q|k|v projection + RoPE epilogue, tcgen05 A-resident)",
+    "gemm_w13_swiglu": "fk::gemm_res_kernel<SWIGLU> (w1|w3 projection + SiLU*mul epilogue, tcgen05 A-resident)",
+    "gemm_dgated_swiglu_bwd": "fk::gemm_res_kernel<SWIGLU_BWD> (d gated GEMM + SwiGLU derivative epilogue)",
+    "gemm_w2": "fk::gemm_stream_kernel (w2 projection, K = hidden)",
+    "gemm_w13_dx": "fk::gemm_stream_kernel (MLP input gradient, K = 2 hidden)",
+    "gemm_qkv_dx": "fk::gemm_stream_kernel (attention input gradient, K = 3 inner)",
+    "gemm_linear": "fk::gemm_res/stream_kernel (nn.Linear forward)",
+    "gemm_linear_dx": "fk::gemm_res/stream_kernel (nn.Linear input gradient)",
+    "gemm_linear_dw": "fk::gemm_tn_kernel (nn.Linear weight gradient)",
+    "gemm_qkv_dw": "fk::gemm_tn_kernel (q|k|v weight gradient)",
+    "gemm_w2_dw": "fk::gemm_tn_kernel (w2 weight gradient)",
+    "gemm_w13_dw": "fk::gemm_tn_kernel (w1|w3 weight gradient)",
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4-joint", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: the workload's batch is the GLOBAL batch, split over the GPUs (accelerate split_batches=True, "
+                         "utils/train_utils.py:100)")
+    ap.add_argument("--grad-comm", default="bf16", choices=["fp32", "bf16"], help="dtype of the DDP gradient buckets on the wire")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--trials", type=int, default=TRIALS_PER_GPU, help="trials per GPU (the metric's config is 128)")
+    ap.add_argument("--no-extras", action="store_true", help="skip gpu_eager_baseline / op table / vq_search_sweep")
+    ap.add_argument("--trials", type=int, default=0, help="trials per GPU (default: the workload's configuration)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -220,15 +515,23 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = args.steps
-    B = args.trials
+    B = args.trials or DEFAULT_TRIALS[args.workload]
+    if args.scaling == "strong":
+        if B % world != 0:
+            raise SystemExit(f"strong scaling: global batch {B} is not divisible by {world} GPUs")
+        B //= world
+    wl = args.workload
 
     torch.manual_seed(1234)       # identical initial weights on every rank
-    model = Joint().to(dev).train()
+    model = build_model(wl).to(dev).train()
     net = model
     if world > 1:
         # VQ buffers are kept identical by the packed EMA all-reduce inside the quantiser, not by DDP broadcasts
         net = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
                                                   gradient_as_bucket_view=True)
+        if args.grad_comm == "bf16":
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
 
@@ -238,6 +541,7 @@ def main():
     host = [(x.pin_memory(), t.pin_memory()) for x, t in host]
     pool = [(x.to(dev), t.to(dev)) for x, t in host]
     h2d_bytes = host[0][0].numel() * 4 + host[0][1].numel() * 4
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8) if h2d_bytes < (140 << 20) else None
 
     def step(x, t):
         opt.zero_grad(set_to_none=True)
@@ -266,6 +570,7 @@ def main():
     assert torch.isfinite(loss).all(), "non-finite loss in warm-up"
 
     # ---- timed region 1: inputs resident in HBM ----
+    small_batch = pool[0][0].numel() * 4 < (130 << 20)
     clocks = ClockSampler(local_rank)
     clocks.start()
     _lib.reset_launch_count()
@@ -273,31 +578,60 @@ def main():
     _lib.TIMER.enabled = True
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        loss = step(*pool[i % n_pool])
-    e1.record()
-    barrier()
+    if small_batch:
+        # inputs smaller than L2: flush it between timed steps and time each step on its own
+        ms_total = 0.0
+        for i in range(K):
+            flush.zero_()
+            e0.record()
+            loss = step(*pool[i % n_pool])
+            e1.record()
+            torch.cuda.synchronize()
+            ms_total += e0.elapsed_time(e1)
+        barrier()
+    else:
+        e0.record()
+        for i in range(K):
+            loss = step(*pool[i % n_pool])
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
     _lib.TIMER.enabled = False
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = max_over_ranks(ms_total)
     launches = _lib.launch_count()
     ksum = _lib.TIMER.summary()
     clk = clocks.stop()
     final_loss = float(loss.detach())
 
-    # ---- timed region 2: end to end (pinned host batch -> device every step, loss read back every step) ----
-    xd = torch.empty_like(pool[0][0])
-    td = torch.empty_like(pool[0][1])
+    # ---- timed region 2: end to end.  Every step copies its pinned host batch to the device (on a copy stream, one
+    #      batch ahead of the compute, double buffered) and reads the loss back (utils/train_utils.py:147) ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(pool[0][0]), torch.empty_like(pool[0][1])) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        hx, ht = host[i % n_pool]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])          # the step that used this buffer two steps ago has finished
+            bufs[i & 1][0].copy_(hx, non_blocking=True)
+            bufs[i & 1][1].copy_(ht, non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
     barrier()
+    for ev in consumed:
+        ev.record()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
+    prefetch(0)
     for i in range(K):
-        hx, ht = host[i % n_pool]
-        xd.copy_(hx, non_blocking=True)
-        td.copy_(ht, non_blocking=True)
-        loss = step(xd, td)
-        _ = loss.item()                          # the trainer logs the loss every step (utils/train_utils.py:147)
+        if i + 1 < K:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i & 1])
+        loss = step(*bufs[i & 1])
+        consumed[i & 1].record()
+        _ = loss.item()                          # the trainer logs the loss every step
     t1.record()
     barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
@@ -309,58 +643,70 @@ def main():
         except Exception:
             pass
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)       # kernel timed inside a long step -> sustained figure
+        tc_burst = peaks.get("bf16_tflops", 1650.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-        n_vq = B * (T_BINS // 4)
-        # ---- per-kernel rooflines from CUDA events recorded around each launch inside the timed region ----
-        dens = (16 + 1) / (2.0 * 16)               # block-causal density with 16 time patches
-        S, H, HD = 4096, 16, 32
-        qk = 2.0 * B * H * S * S * HD * dens       # flops of ONE score-shaped matmul over the visible pairs
-        # algorithmic flops per launch: fwd = QK^T + PV; dK/dV kernel = S, dP, dV, dK; the dQ kernel owes only dQ
-        # (its S / dP re-computation is overhead of the two-kernel split and is not counted as useful work)
-        alg = {"vq_search": 2.0 * n_vq * VQ_K * VQ_D, "attn_fwd": 2 * qk, "attn_bwd_dkv": 4 * qk, "attn_bwd_dq": 1 * qk}
-        names = {"vq_search": "fk::vq_search_kernel (tcgen05/TMEM/TMA nearest-codeword search)",
-                 "attn_fwd": "fk::attn_fwd_tc_kernel (label-mask flash attention forward, tcgen05/TMEM/TMA)",
-                 "attn_bwd_dkv": "fk::attn_bwd_tc_kernel<DKV> (label-mask flash attention dK/dV, tcgen05/TMEM/TMA)",
-                 "attn_bwd_dq": "fk::attn_bwd_tc_kernel<DQ> (label-mask flash attention dQ, tcgen05/TMEM/TMA)"}
-        # ncu --set full captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
-        traffic = {"vq_search": NCU_TRAFFIC.get("vq_search")}
-        traffic.update({k: int(v * B / 16) for k, v in NCU_TRAFFIC_PER_16_TRIALS.items()})
+        # ---- per-kernel rooflines from CUDA events recorded around each launch inside the timed region; the algorithmic
+        #      flops of a launch are recorded with it (attention: 2 flops x visible (q, k) pairs x 32 per score-shaped matmul;
+        #      fwd = 2 matmuls; dK/dV kernel = 4 (S, dP, dV, dK); the dQ kernel owes 1 (its S / dP recompute is overhead)) ----
+        traffic = {"vq_search": NCU_TRAFFIC.get("vq_search") if wl == "cfg4-joint" else None}
+        if wl in ("cfg4-joint", "cfg2-encoder"):
+            traffic.update({k: int(v * B / 16) for k, v in NCU_TRAFFIC_PER_16_TRIALS.items()})
         kern = {}
-        for name, flops in alg.items():
-            if name not in ksum:
+        for name, (n, ms, work) in ksum.items():
+            if work <= 0 or ms <= 0:
                 continue
-            n, ms, _ = ksum[name]
-            big = [1] if name == "vq_search" else None
             avg_ms = ms / n
-            ach = flops / (avg_ms * 1e-3) / 1e12
-            kern[name] = {"kernel": names[name], "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
-                          "frac": ach / tc_peak, "traffic": traffic.get(name), "algorithmic_flops_per_launch": flops,
-                          "avg_launch_ms": avg_ms, "launches_timed": n, "ms_per_step": ms / K, "peak_source": peak_src}
-        # the roofline object is the kernel with the largest share of the step
+            ach = work / (ms * 1e-3) / 1e12
+            kern[name] = {"kernel": KERNEL_NAMES.get(name, name), "bound": "tensor", "achieved": ach, "peak": tc_peak,
+                          "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": traffic.get(name),
+                          "algorithmic_flops_per_launch": work / n, "avg_launch_ms": avg_ms, "launches_timed": n,
+                          "ms_per_step": ms / K, "peak_source": peak_src}
         roof = None
         if kern:
             dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
             roof = dict(kern[dom])
             roof["share_of_step"] = roof["ms_per_step"] / (ms_total / K)
+        groups = {}
+        for name, v in kern.items():
+            grp = "attention" if name.startswith("attn") else ("gemm" if name.startswith("gemm") else name)
+            groups[grp] = groups.get(grp, 0.0) + v["ms_per_step"]
         total_trials = B * world * K
         line = {
-            "metric": "trials/sec VQ+Brainformer train step", "value": total_trials / (ms_total * 1e-3), "unit": "trials/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "trials_per_gpu": B, "global_batch": B * world, "bins": T_BINS, "parallelism": f"dp{world}",
-                       "l2_policy": "inputs larger than L2 (134 MB batch rotated over a 3-batch pool)"},
+            "metric": METRIC, "value": total_trials / (ms_total * 1e-3), "unit": "trials/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOADS[wl], "trials_per_gpu": B, "global_batch": B * world, "bins": T_BINS,
+                       "parallelism": f"dp{world}", "grad_comm": args.grad_comm if world > 1 else None,
+                       "l2_policy": ("L2 flushed (256 MB write) between individually timed steps" if small_batch else
+                                     "inputs larger than L2 (134 MB batch rotated over a 3-batch pool)")},
             "clocks": clk,
             "e2e": {"value": total_trials / (ms_e2e * 1e-3), "unit": "trials/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
+                    "how": "pinned host batch -> device on a copy stream one batch ahead (double buffered), loss.item() every step"},
             "gpu_launches": int(launches),
             "loss": final_loss,
             "roofline": roof,
             "vq_search": kern.get("vq_search"),
             "kernels": kern,
+            "ms_per_step_by_group": groups,
         }
+        if world == 1 and not args.no_extras:
+            del pool, bufs
+            torch.cuda.empty_cache()
+            try:
+                eager_trials = {"cfg4-joint": 8, "cfg2-encoder": 8, "cfg3-mae": 8, "cfg3-simple-mae": 64, "cfg1-vqvae": 32}[wl]
+                line["gpu_eager_baseline"] = gpu_eager_run(wl, dev, eager_trials)
+                if wl == "cfg4-joint":
+                    line["gpu_eager_baseline"]["per_op"] = eager_op_table(dev)
+                    line["vq_search_sweep"] = {"N": 16384, "D": 256, "peak": tc_burst, "peak_source": "MEASURED_PEAKS.json bf16_tflops "
+                                               "(burst: kernel timed alone, L2 flushed between launches)",
+                                               "points": vq_search_sweep(dev, tc_burst)}
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"], _ = cpu_reference_run(steps=2, warmup=1)
+                trials = 32 if wl == "cfg1-vqvae" else (8 if wl == "cfg3-simple-mae" else CPU_SAMPLE_TRIALS)
+                line["cpu_baseline"], _ = cpu_reference_run(wl, steps=2, warmup=1, trials=trials)
             except Exception as e:  # the number is informational; never lose the GPU line over it
                 line["cpu_baseline"] = {"value": None, "unit": "trials/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {type(e).__name__}: {e}"}

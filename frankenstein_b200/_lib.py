@@ -179,7 +179,7 @@ class KernelTimer:
         out = {}
         for name, a, b, work in self.records:
             n, ms, w = out.get(name, (0, 0.0, 0.0))
-            out[name] = (n + 1, ms + a.elapsed_time(b), w + work)
+            out[name] = (n + 1, ms + a.elapsed_time(b), w + float(work))      # (work may be a 0-dim device tensor)
         return out
 
 

@@ -26,8 +26,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+import os
+
+from . import gemm, ops
 from .ops import LabelMask, RopeSpec
+
+# "own" (default): the dense projections run on the library's tcgen05 GEMMs with fused epilogues (csrc/gemm.cu);
+# "cublas": the same math through F.linear + the separate RoPE / SwiGLU kernels (A/B comparison only).
+GEMM_IMPL = os.environ.get("FK_GEMM", "own")
 
 try:  # the reference derives its configs from simple_parsing's Serializable; optional here
     from simple_parsing.helpers import Serializable as _ConfigBase
@@ -96,6 +102,9 @@ def _linear_bf16(x, weight, bias=None):
     """bf16 GEMM regardless of the caller's autocast dtype: the reference trainer runs fp16 autocast
     (utils/train_utils.py:96), under which F.linear would re-cast the bf16 operands to fp16 and hand fp16 activations to
     kernels that take bf16.  The compute dtype of this package is bf16 (fp32 accumulate) whatever autocast says."""
+    if GEMM_IMPL == "own" and x.is_cuda and gemm.linear_supported(weight.shape[1], weight.shape[0]):
+        return gemm.linear(x, weight, bias)
+    # shapes outside the kernels' granularity (e.g. the 32-wide patch projections) stay on the library GEMM
     with torch.autocast("cuda", enabled=False):
         return F.linear(x.to(BF16), weight.to(BF16), None if bias is None else bias.to(BF16))
 
@@ -112,6 +121,10 @@ class MLP(nn.Module):
     def forward(self, x) -> torch.Tensor:
         if not x.is_cuda:
             raise ops.FkError("frankenstein_b200 modules run on a B200 only (no CPU fallback)")
+        hidden, dim = self.w1.weight.shape
+        if GEMM_IMPL == "own" and gemm.mlp_supported(dim, hidden):
+            # w1 | w3 as one tcgen05 GEMM whose epilogue forms the gate; backward fuses the SwiGLU derivative likewise
+            return gemm.swiglu_mlp(x, self.w1.weight, self.w3.weight, self.w2.weight)
         w13 = torch.cat([self.w1.weight, self.w3.weight], dim=0)
         gated = ops.swiglu(_linear_bf16(x, w13))
         return _linear_bf16(gated, self.w2.weight)
@@ -145,13 +158,19 @@ class CausalSelfAttention(nn.Module):
         if not x.is_cuda:
             raise ops.FkError("frankenstein_b200 modules run on a B200 only (no CPU fallback)")
         B, T, _ = x.shape
-        wqkv = torch.cat([self.qw.weight, self.kw.weight, self.vw.weight], dim=0)
-        qkv = _linear_bf16(x, wqkv)
         spec = rope
         if isinstance(rope, torch.Tensor) and rope.dim() == 2 and self.head_dim == 32:
             spec = RopeSpec.from_complex(rope, T, last=True)           # reference convention: rope[-T:]
         kernel_ok = (self.head_dim == 32 and (attn_mask is None or isinstance(attn_mask, LabelMask))
                      and (spec is None or isinstance(spec, RopeSpec)))
+        inner, dim = self.qw.weight.shape
+        if kernel_ok and GEMM_IMPL == "own" and gemm.qkv_supported(dim, inner):
+            # one tcgen05 GEMM for q | k | v with RoPE applied to q and k in its epilogue (no separate rope pass)
+            qkv = gemm.qkv_rope(x, self.qw.weight, self.kw.weight, self.vw.weight, spec, self.n_heads)
+            res = ops.attention_qkv(qkv, self.n_heads, spec, attn_mask, rope_applied=True)
+            return _linear_bf16(res, self.project.weight)
+        wqkv = torch.cat([self.qw.weight, self.kw.weight, self.vw.weight], dim=0)
+        qkv = _linear_bf16(x, wqkv)
         if kernel_ok:
             res = ops.attention_qkv(qkv, self.n_heads, spec, attn_mask)
         else:

@@ -1,0 +1,760 @@
+// Dense bf16 GEMMs of the transformer blocks on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM,
+// operands staged by TMA), with the elementwise work that follows each projection fused into the epilogue.
+//
+// Replaces (reference call sites, models/brainformer.py): the bias-free Linears qw / kw / vw (:141-143, one fused
+// projection) with apply_rope (:70-91, :156-158) in the epilogue; project (:171); the SwiGLU MLP w1 / w3 (:119-124, one
+// fused projection whose epilogue forms silu(w1 x) * (w3 x)) and w2; and their autograd: dX = dY W (same kernel on a
+// transposed weight copy; the MLP's dgated GEMM applies the SwiGLU backward in its epilogue) and dW = dY^T X (fk_gemm_tn,
+// both operands read MN-major straight from the row-major activations, split over the token dimension).
+//
+// Three kernels, all persistent (one CTA per SM), warp-specialised like vq_search.cu: warp 0 = TMA producer,
+// warp 1 = MMA issuer (whole-warp loop, one elected lane issues), warp 2 = TMEM allocator, warps 4-11 = epilogue.
+//
+//   gemm_res_kernel   C[M,N] = A[M,K] B[N,K]^T, K <= 512.  The A row block (128 rows x K) stays RESIDENT in shared memory
+//                     for all N tiles of the block, only B streams (256-column tiles, 32 KB k-slabs through an mbarrier
+//                     ring), accumulators double buffered in TMEM (2 x 256 columns) so the epilogue of tile j overlaps the
+//                     MMAs of tile j+1.  The next block's A slabs are loaded one by one as the last tile releases them.
+//   gemm_stream_kernel  same product for long K: 256 x 256 tiles (two M=128 halves share each B slab), both operands
+//                     streamed, the 512 TMEM columns hold one tile (the epilogue is exposed once per long K loop).
+//   gemm_tn_kernel    out[Na,Nb] (fp32) = A[M,Na]^T B[M,Nb] over a range of rows: 256 x 256 tiles, both operands MN-major
+//                     (64-column chunks of 64 rows, 128-byte swizzle), partial sums per row range written to a workspace
+//                     and added up in a fixed order by gemm_tn_reduce_kernel (deterministic, no atomics).
+//
+// L2 -> SM traffic bounds these shapes as much as the tensor pipe does (K is only 512..4096): a 128-row resident block or
+// a 256 x 256 streamed tile needs one operand byte per 128 flops, about what the L2 fabric delivers at the bf16 peak.
+#include "common.cuh"
+#include "fk_b200.h"
+#include "tma_host.cuh"
+
+namespace fk {
+
+constexpr int kGemmThreads = 384;          // 4 control warps + 8 epilogue warps
+constexpr int kASlabBytes = 128 * 128;     // 128 rows x 64 bf16
+constexpr int kBSlabBytes = 256 * 128;     // 256 rows x 64 bf16
+constexpr int kGemmSmemLimit = 232448 - 1024;
+
+enum { EPI_STORE = 0, EPI_ROPE = 1, EPI_SWIGLU = 2, EPI_SWIGLU_BWD = 3 };
+
+struct GemmParams {
+  __nv_bfloat16* C;          // [M, N] (EPI_SWIGLU: the fused projection h13; EPI_SWIGLU_BWD: unused)
+  long long ldc;
+  __nv_bfloat16* C2;         // EPI_SWIGLU: gated [M, N/2]; EPI_SWIGLU_BWD: dh13 [M, 2N]
+  long long ldc2;
+  const __nv_bfloat16* aux;  // EPI_SWIGLU_BWD: h13 [M, 2N]
+  long long ld_aux;
+  const float* bias;         // [N] or null (EPI_STORE)
+  const float2* rope_table;  // EPI_ROPE: [rope_len][16] (cos, sin)
+  const int* rope_pos;       // [M] or null: position of row m = rope_pos ? rope_pos[m] : (m % rope_S) + rope_offset
+  int rope_len, rope_offset, rope_cols, rope_S;
+  long long M;
+  int N, K, nslab, ntile, nstage;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&a)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                 "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]),
+                 "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
+               :: "memory");
+}
+
+// MN-major operand tile written by TMA with the 128-byte swizzle as [chunk][64 k-rows][64 elements]: the canonical
+// layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- LBO = distance between 64-element chunks along M/N,
+// SBO = distance between 8-row groups along K (1024 B).  A K step of 16 rows adds 2048 B to the start address.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// 32 fp32 accumulator columns of one row -> 32 bf16 (64 bytes) at dst (16-byte aligned)
+__device__ __forceinline__ void store32_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    *reinterpret_cast<uint4*>(dst + i * 8) =
+        make_uint4(pack_bf16(v[i * 8], v[i * 8 + 1]), pack_bf16(v[i * 8 + 2], v[i * 8 + 3]),
+                   pack_bf16(v[i * 8 + 4], v[i * 8 + 5]), pack_bf16(v[i * 8 + 6], v[i * 8 + 7]));
+  }
+}
+__device__ __forceinline__ void load32_bf16(const __nv_bfloat16* src, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 w = *reinterpret_cast<const uint4*>(src + i * 8);
+    v[i * 8] = bf16_lo(w.x); v[i * 8 + 1] = bf16_hi(w.x); v[i * 8 + 2] = bf16_lo(w.y); v[i * 8 + 3] = bf16_hi(w.y);
+    v[i * 8 + 4] = bf16_lo(w.z); v[i * 8 + 5] = bf16_hi(w.z); v[i * 8 + 6] = bf16_lo(w.w); v[i * 8 + 7] = bf16_hi(w.w);
+  }
+}
+__device__ __forceinline__ void to_f32(const uint32_t (&r)[32], float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.f / (1.f + __expf(-x)); }
+
+struct GemmSmem {
+  uint64_t* bars;
+};
+
+// ================================================================================================
+// A-resident kernel (K <= 512)
+// ================================================================================================
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* As = smem;                                        // nslab x 16 KB
+  uint8_t* Bs = As + p.nslab * kASlabBytes;                  // nstage x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + p.nstage * kBSlabBytes);
+  uint64_t* a_full = bars;            // [8]
+  uint64_t* a_empty = bars + 8;       // [8]
+  uint64_t* b_full = bars + 16;       // [8]
+  uint64_t* b_empty = bars + 24;      // [8]
+  uint64_t* tmem_full = bars + 32;    // [2]
+  uint64_t* tmem_empty = bars + 34;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+      mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_blocks = static_cast<int>((p.M + 127) / 128);
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    int stage = 0;
+    uint32_t phase = 0, it = 0;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+      for (int t = 0; t < p.ntile; ++t) {
+        for (int ks = 0; ks < p.nslab; ++ks) {
+          if (t == 0) {
+            // A slab ks of this block: free once the last tile of the previous block has consumed it
+            mbar_wait(&a_empty[ks], (it & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&a_full[ks], kASlabBytes);
+              tma_load_2d(As + ks * kASlabBytes, &tm_a, &a_full[ks], ks * 64, blk * 128);
+            }
+            __syncwarp();
+          }
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&b_full[stage], kBSlabBytes);
+            tma_load_2d(Bs + stage * kBSlabBytes, &tm_b, &b_full[stage], ks * 64, t * 256);
+          }
+          __syncwarp();
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t as_addr = smem_u32(As), bs_addr = smem_u32(Bs);
+    int stage = 0;
+    uint32_t phase = 0, it = 0, tc = 0;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+      for (int t = 0; t < p.ntile; ++t, ++tc) {
+        const uint32_t as = tc & 1;
+        mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + as * 256;
+        for (int ks = 0; ks < p.nslab; ++ks) {
+          if (t == 0) mbar_wait(&a_full[ks], it & 1);
+          mbar_wait(&b_full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(as_addr + ks * kASlabBytes);
+          const uint64_t bdesc = umma_desc_sw128(bs_addr + stage * kBSlabBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (ks | kk) != 0);
+            umma_commit(&b_empty[stage]);
+            if (t == p.ntile - 1) umma_commit(&a_empty[ks]);
+          }
+          __syncwarp();
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&tmem_full[as]);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int e = warp - 4;
+    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    const int ch = e >> 2;           // column half of the 256-column tile
+    uint32_t tc = 0;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+      const long long row = static_cast<long long>(blk) * 128 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float2 cs[16];
+      if (EPI == EPI_ROPE) {
+        int ps = 0;
+        if (row_ok) ps = p.rope_pos ? p.rope_pos[row] : static_cast<int>(row % p.rope_S) + p.rope_offset;
+        ps = min(max(ps, 0), p.rope_len - 1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cs[i] = __ldg(p.rope_table + static_cast<long long>(ps) * 16 + i);
+      }
+      for (int t = 0; t < p.ntile; ++t, ++tc) {
+        const uint32_t as = tc & 1;
+        mbar_wait(&tmem_full[as], (tc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+        const int n0 = t * 256;
+        auto release = [&]() {           // every TMEM read of this accumulator stage by this warp has completed
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        };
+        if (EPI == EPI_STORE || EPI == EPI_ROPE) {
+          uint32_t r[2][32];
+          tmem_ld32(taddr + ch * 128, r[0]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_wait_ld32(r[c & 1]);
+            if (c < 3) tmem_ld32(taddr + ch * 128 + (c + 1) * 32, r[(c + 1) & 1]);
+            else release();
+            const int col = n0 + ch * 128 + c * 32;
+            float v[32];
+            to_f32(r[c & 1], v);
+            if (EPI == EPI_ROPE) {
+              if (col < p.rope_cols) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float x0 = v[2 * i], x1 = v[2 * i + 1];
+                  v[2 * i] = x0 * cs[i].x - x1 * cs[i].y;
+                  v[2 * i + 1] = x0 * cs[i].y + x1 * cs[i].x;
+                }
+              }
+            } else if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += (col + i < p.N) ? __ldg(p.bias + col + i) : 0.f;
+            }
+            if (row_ok && col < p.N) store32_bf16(p.C + row * p.ldc + col, v);      // (N % 32 == 0 is required)
+          }
+        } else if (EPI == EPI_SWIGLU) {
+          // tile columns: [0,128) = w1 block, [128,256) = w3 block of the same 128 hidden units (weights interleaved by the
+          // host in blocks of 128).  This warp: hidden units ch*64 .. ch*64+63 of the block.
+          uint32_t ra[32], rb[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(taddr + ch * 64 + c * 32, ra);
+            tmem_ld32(taddr + 128 + ch * 64 + c * 32, rb);
+            tmem_wait_ld32(ra);
+            tmem_wait_ld32(rb);
+            if (c == 1) release();
+            float a[32], b[32], g[32];
+            to_f32(ra, a);
+            to_f32(rb, b);
+            const int ca = n0 + ch * 64 + c * 32;                 // column of the w1 part inside h13
+            if (row_ok && ca < p.N) {
+              // the saved h13 is bf16: gate from the ROUNDED values, so that backward (which reads h13) sees the same function
+              store32_bf16(p.C + row * p.ldc + ca, a);
+              store32_bf16(p.C + row * p.ldc + ca + 128, b);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float h1 = __bfloat162float(__float2bfloat16_rn(a[i])), h3 = __bfloat162float(__float2bfloat16_rn(b[i]));
+                g[i] = h1 * sigmoidf_fast(h1) * h3;
+              }
+              store32_bf16(p.C2 + row * p.ldc2 + (n0 >> 1) + ch * 64 + c * 32, g);
+            }
+          }
+        } else {   // EPI_SWIGLU_BWD: accumulator = d gated [M, N]; this warp: hidden block n0/128 + ch (128 units)
+          uint32_t r[2][32];
+          tmem_ld32(taddr + ch * 128, r[0]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_wait_ld32(r[c & 1]);
+            if (c < 3) tmem_ld32(taddr + ch * 128 + (c + 1) * 32, r[(c + 1) & 1]);
+            else release();
+            const int col = n0 + ch * 128 + c * 32;               // hidden unit
+            if (row_ok && col < p.N) {
+              const long long o = 2ll * (n0 + ch * 128) + c * 32;    // column of h1 inside the interleaved h13 / dh13
+              float dg[32], h1[32], h3[32], d1[32], d3[32];
+              to_f32(r[c & 1], dg);
+              load32_bf16(p.aux + row * p.ld_aux + o, h1);
+              load32_bf16(p.aux + row * p.ld_aux + o + 128, h3);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float s = sigmoidf_fast(h1[i]);
+                const float silu = h1[i] * s;
+                d1[i] = dg[i] * h3[i] * (s + silu * (1.f - s));     // d silu(x)/dx = s + x s (1 - s)
+                d3[i] = dg[i] * silu;
+              }
+              store32_bf16(p.C2 + row * p.ldc2 + o, d1);
+              store32_bf16(p.C2 + row * p.ldc2 + o + 128, d3);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ================================================================================================
+// Streaming kernel (long K): 256 x 256 tiles, EPI_STORE (+ bias)
+// ================================================================================================
+constexpr int kStreamStageBytes = 2 * kASlabBytes + kBSlabBytes;     // 64 KB: A rows 0-255 | B rows 0-255
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstage * kStreamStageBytes);
+  uint64_t* full = bars;              // [4]
+  uint64_t* empty = bars + 4;         // [4]
+  uint64_t* tmem_full = bars + 8;     // [1]
+  uint64_t* tmem_empty = bars + 9;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_rb = (p.M + 255) / 256;
+  const long long n_units = n_rb * p.ntile;     // unit u: row block u / ntile, column tile u % ntile
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int rb = static_cast<int>(u / p.ntile), t = static_cast<int>(u % p.ntile);
+      for (int ks = 0; ks < p.nslab; ++ks) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* st = smem + stage * kStreamStageBytes;
+          mbar_expect_tx(&full[stage], kStreamStageBytes);
+          tma_load_2d(st, &tm_a, &full[stage], ks * 64, rb * 256);                       // box 64 x 256 rows
+          tma_load_2d(st + 2 * kASlabBytes, &tm_b, &full[stage], ks * 64, t * 256);
+        }
+        __syncwarp();
+        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t s_addr = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0, uc = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+      mbar_wait(tmem_empty, (uc & 1) ^ 1);
+      tc_fence_after();
+      for (int ks = 0; ks < p.nslab; ++ks) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t st = s_addr + stage * kStreamStageBytes;
+        const uint64_t a0 = umma_desc_sw128(st), a1 = umma_desc_sw128(st + kASlabBytes);
+        const uint64_t bdesc = umma_desc_sw128(st + 2 * kASlabBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_u, a0 + 2 * kk, bdesc + 2 * kk, idesc, (ks | kk) != 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_u + 256, a1 + 2 * kk, bdesc + 2 * kk, idesc, (ks | kk) != 0);
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(tmem_full);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4;
+    const int q = warp & 3, h = e >> 2;           // lane quarter, row half
+    uint32_t uc = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+      const int rb = static_cast<int>(u / p.ntile), t = static_cast<int>(u % p.ntile);
+      const long long row = static_cast<long long>(rb) * 256 + h * 128 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(tmem_full, uc & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256;
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        tmem_wait_ld32(r[c & 1]);
+        if (c < 7) {
+          tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        const int col = t * 256 + c * 32;
+        float v[32];
+        to_f32(r[c & 1], v);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += (col + i < p.N) ? __ldg(p.bias + col + i) : 0.f;
+        }
+        if (row_ok && col < p.N) store32_bf16(p.C + row * p.ldc + col, v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ================================================================================================
+// TN kernel: out[Na, Nb] = A[M, Na]^T B[M, Nb] (fp32 partial sums per row range)
+// ================================================================================================
+struct TnParams {
+  float* ws;                 // [splits][Na][Nb]
+  long long M;
+  int Na, Nb, ta, tb, splits, nstage;
+  long long rows_per_split;  // multiple of 64
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const TnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  constexpr int kStage = 2 * kBSlabBytes;      // A: 4 chunks x 8 KB | B: 4 chunks x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstage * kStage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 4;
+  uint64_t* tmem_full = bars + 8;
+  uint64_t* tmem_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit u -> (split, tile): consecutive CTAs work on the SAME row range and different output tiles, so a row range of
+  // the activations is fetched from HBM once and served to the other tiles from L2
+  const int n_tiles = p.ta * p.tb;
+  const long long n_units = static_cast<long long>(n_tiles) * p.splits;
+  auto k_range = [&](int split, long long& k0, long long& k1) {
+    k0 = split * p.rows_per_split;
+    k1 = min(p.M, k0 + p.rows_per_split);
+  };
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int split = static_cast<int>(u / n_tiles), tile = static_cast<int>(u % n_tiles);
+      const int ia = tile / p.tb, ib = tile % p.tb;
+      long long k0, k1;
+      k_range(split, k0, k1);
+      for (long long k = k0; k < k1; k += 64) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* st = smem + stage * kStage;
+          mbar_expect_tx(&full[stage], kStage);
+          tma_load_3d(st, &tm_a, &full[stage], 0, static_cast<int>(k), ia * 4);              // box 64 x 64 rows x 4 chunks
+          tma_load_3d(st + kBSlabBytes, &tm_b, &full[stage], 0, static_cast<int>(k), ib * 4);
+        }
+        __syncwarp();
+        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256) | (1u << 15) | (1u << 16);     // A and B MN-major
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t s_addr = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0, uc = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+      const int split = static_cast<int>(u / n_tiles);
+      long long k0, k1;
+      k_range(split, k0, k1);
+      mbar_wait(tmem_empty, (uc & 1) ^ 1);
+      tc_fence_after();
+      bool first = true;
+      for (long long k = k0; k < k1; k += 64) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t st = s_addr + stage * kStage;
+        const uint64_t a0 = umma_desc_mn_sw128(st, 8192), a1 = umma_desc_mn_sw128(st + 2 * 8192, 8192);
+        const uint64_t bdesc = umma_desc_mn_sw128(st + kBSlabBytes, 8192);
+        if (elect_one()) {
+          // a K step of 16 rows = 2048 B = +128 in the (address >> 4) field
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_u, a0 + 128 * kk, bdesc + 128 * kk, idesc, !(first && kk == 0));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_u + 256, a1 + 128 * kk, bdesc + 128 * kk, idesc, !(first && kk == 0));
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        first = false;
+        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(tmem_full);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4;
+    const int q = warp & 3, h = e >> 2;
+    uint32_t uc = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+      const int split = static_cast<int>(u / n_tiles), tile = static_cast<int>(u % n_tiles);
+      const int ia = tile / p.tb, ib = tile % p.tb;
+      long long k0, k1;
+      k_range(split, k0, k1);
+      const int row = ia * 256 + h * 128 + q * 32 + lane;        // index along Na
+      const bool row_ok = row < p.Na;
+      float* dst = p.ws + (static_cast<long long>(split) * p.Na + row) * p.Nb + ib * 256;
+      // (the host never creates an empty row range: fk_gemm_tn_splits drops splits that would be empty)
+      mbar_wait(tmem_full, uc & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256;
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        tmem_wait_ld32(r[c & 1]);
+        if (c < 7) {
+          tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        if (row_ok && ib * 256 + c * 32 < p.Nb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(dst + c * 32 + i * 4) =
+                make_uint4(r[c & 1][i * 4], r[c & 1][i * 4 + 1], r[c & 1][i * 4 + 2], r[c & 1][i * 4 + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+__global__ void __launch_bounds__(256)
+gemm_tn_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long long n4, int splits) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = *reinterpret_cast<const float4*>(ws + i * 4);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = ldg_nc_f4(ws + (static_cast<long long>(s) * n4 + i) * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i * 4) = acc;
+}
+
+}  // namespace fk
+
+using namespace fk;
+
+#define FK_API extern "C" __attribute__((visibility("default")))
+
+template <class Kern>
+static int set_smem_attr(Kern* kern, bool& done, int bytes) {
+  if (done) return FK_OK;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
+    return FK_ERR_CUDA;
+  }
+  done = true;
+  return FK_OK;
+}
+
+FK_API int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, long long M, int N,
+                      int K, const float* bias, int epilogue, void* C2, long long ldc2, const void* aux, long long ld_aux,
+                      const float* rope_table, int rope_len, const int* rope_pos, int rope_offset, int rope_cols, int rope_S,
+                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(A && B && M > 0 && N > 0 && K > 0, "fk_gemm_nt: bad argument");
+  FK_REQUIRE(M < (1ll << 31) - 256, "fk_gemm_nt: too many rows");
+  FK_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "fk_gemm_nt: K and the leading dimensions must be multiples of 8 (16-byte rows)");
+  FK_REQUIRE(N % 32 == 0, "fk_gemm_nt: N must be a multiple of 32");
+  FK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "fk_gemm_nt: operands must be 16-byte aligned");
+  FK_REQUIRE(epilogue >= EPI_STORE && epilogue <= EPI_SWIGLU_BWD, "fk_gemm_nt: unknown epilogue");
+  GemmParams p = {};
+  p.C = static_cast<__nv_bfloat16*>(C); p.ldc = ldc;
+  p.C2 = static_cast<__nv_bfloat16*>(C2); p.ldc2 = ldc2;
+  p.aux = static_cast<const __nv_bfloat16*>(aux); p.ld_aux = ld_aux;
+  p.bias = bias;
+  p.rope_table = reinterpret_cast<const float2*>(rope_table); p.rope_pos = rope_pos; p.rope_len = rope_len;
+  p.rope_offset = rope_offset; p.rope_cols = rope_cols; p.rope_S = rope_S;
+  p.M = M; p.N = N; p.K = K;
+  p.nslab = (K + 63) / 64;
+  p.ntile = (N + 255) / 256;
+  if (epilogue == EPI_STORE || epilogue == EPI_ROPE || epilogue == EPI_SWIGLU)
+    FK_REQUIRE(C && ldc % 8 == 0 && ldc >= N && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "fk_gemm_nt: C must be 16-byte aligned with ldc % 8 == 0");
+  if (epilogue == EPI_ROPE) {
+    FK_REQUIRE(rope_table && rope_len > 0 && rope_cols % 32 == 0 && rope_cols <= N && (rope_pos || rope_S > 0), "fk_gemm_nt: bad rope arguments");
+    FK_REQUIRE(rope_pos != nullptr || (rope_offset >= 0 && static_cast<long long>(rope_offset) + (M < rope_S ? M : rope_S) <= rope_len),
+               "fk_gemm_nt: token positions fall outside the rope table");
+  }
+  if (epilogue == EPI_SWIGLU)
+    FK_REQUIRE(N % 256 == 0 && C2 && ldc2 % 8 == 0 && ldc2 >= N / 2 && bias == nullptr, "fk_gemm_nt: SwiGLU epilogue needs N % 256 == 0 and the gated output");
+  if (epilogue == EPI_SWIGLU_BWD)
+    FK_REQUIRE(N % 128 == 0 && C2 && aux && ldc2 % 8 == 0 && ld_aux % 8 == 0 && ldc2 >= 2 * N && ld_aux >= 2 * N && bias == nullptr,
+               "fk_gemm_nt: SwiGLU-backward epilogue needs N % 128 == 0, h13 and dh13");
+  FK_REQUIRE(bias == nullptr || epilogue == EPI_STORE, "fk_gemm_nt: bias goes with the plain epilogue");
+
+  CUtensorMap ta, tb;
+  const int dev = fk_device_ordinal();
+  const int G = fk_sm_count();
+  if (K <= 512) {
+    int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 128);
+    rc |= make_tmap_bf16_2d(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 256);
+    if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
+    int nstage = (kGemmSmemLimit - 512 - p.nslab * kASlabBytes) / kBSlabBytes;
+    if (nstage > 6) nstage = 6;
+    p.nstage = nstage;
+    const int smem_bytes = p.nslab * kASlabBytes + nstage * kBSlabBytes + 512;
+    const long long n_blocks = (M + 127) / 128;
+    const unsigned grid = static_cast<unsigned>(n_blocks < G ? n_blocks : G);
+    static bool done[4][FK_MAX_DEVICES];
+    int r2 = FK_OK;
+    switch (epilogue) {
+      case EPI_STORE:
+        if ((r2 = set_smem_attr(gemm_res_kernel<EPI_STORE>, done[0][dev], kGemmSmemLimit)) != FK_OK) return r2;
+        gemm_res_kernel<EPI_STORE><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+        break;
+      case EPI_ROPE:
+        if ((r2 = set_smem_attr(gemm_res_kernel<EPI_ROPE>, done[1][dev], kGemmSmemLimit)) != FK_OK) return r2;
+        gemm_res_kernel<EPI_ROPE><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+        break;
+      case EPI_SWIGLU:
+        if ((r2 = set_smem_attr(gemm_res_kernel<EPI_SWIGLU>, done[2][dev], kGemmSmemLimit)) != FK_OK) return r2;
+        gemm_res_kernel<EPI_SWIGLU><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+        break;
+      default:
+        if ((r2 = set_smem_attr(gemm_res_kernel<EPI_SWIGLU_BWD>, done[3][dev], kGemmSmemLimit)) != FK_OK) return r2;
+        gemm_res_kernel<EPI_SWIGLU_BWD><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+        break;
+    }
+  } else {
+    FK_REQUIRE(epilogue == EPI_STORE, "fk_gemm_nt: fused epilogues need K <= 512 (the A-resident kernel)");
+    int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 256);
+    rc |= make_tmap_bf16_2d(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 256);
+    if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
+    p.nstage = 3;
+    const int smem_bytes = p.nstage * kStreamStageBytes + 512;
+    const long long n_units = ((M + 255) / 256) * p.ntile;
+    const unsigned grid = static_cast<unsigned>(n_units < G ? n_units : G);
+    static bool done[FK_MAX_DEVICES];
+    const int r2 = set_smem_attr(gemm_stream_kernel, done[dev], kGemmSmemLimit);
+    if (r2 != FK_OK) return r2;
+    gemm_stream_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+  }
+  FK_CHECK_LAUNCH();
+  fk_count_launch(1);
+  return FK_OK;
+}
+
+// number of row ranges fk_gemm_tn splits the contraction into (workspace = splits * Na * Nb floats)
+FK_API int fk_gemm_tn_splits(long long M, int Na, int Nb, int max_ctas) {
+  if (M <= 0 || Na <= 0 || Nb <= 0) return FK_ERR_BAD_ARG;
+  const long long tiles = static_cast<long long>((Na + 255) / 256) * ((Nb + 255) / 256);
+  long long G = max_ctas;
+  if (G <= 0) G = fk_sm_count();
+  if (G <= 0) G = 148;
+  const long long max_splits = (M + 63) / 64;
+  long long best = 1;
+  double best_eff = 0.0;
+  for (int w = 1; w <= 3; ++w) {
+    long long s = (G * w) / tiles;
+    if (s < 1) s = 1;
+    if (s > max_splits) s = max_splits;
+    if (s > 64) s = 64;
+    const long long units = tiles * s;
+    const double eff = static_cast<double>(units) / (static_cast<double>((units + G - 1) / G) * G);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  // rows per split are rounded up to 64: drop splits that would be empty
+  const long long rps = ((M + best - 1) / best + 63) / 64 * 64;
+  return static_cast<int>((M + rps - 1) / rps);
+}
+
+FK_API int fk_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* out, long long M, int Na, int Nb,
+                      float* ws, int splits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(A && B && out && ws && M > 0 && Na > 0 && Nb > 0, "fk_gemm_tn: bad argument");
+  FK_REQUIRE(M < (1ll << 31) - 64, "fk_gemm_tn: too many rows");
+  FK_REQUIRE(Na % 64 == 0 && Nb % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= Na && ldb >= Nb,
+             "fk_gemm_tn: Na and Nb must be multiples of 64, leading dimensions multiples of 8");
+  FK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0, "fk_gemm_tn: pointers must be 16-byte aligned");
+  const int G = fk_sm_count();
+  FK_REQUIRE(G > 0 && splits == fk_gemm_tn_splits(M, Na, Nb, G), "fk_gemm_tn: split count does not match fk_gemm_tn_splits");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_chunks(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(Na), static_cast<uint64_t>(lda));
+  rc |= make_tmap_bf16_chunks(&tb, B, static_cast<uint64_t>(M), static_cast<uint64_t>(Nb), static_cast<uint64_t>(ldb));
+  if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
+  TnParams p = {};
+  p.ws = ws; p.M = M; p.Na = Na; p.Nb = Nb; p.ta = (Na + 255) / 256; p.tb = (Nb + 255) / 256; p.splits = splits;
+  p.rows_per_split = ((M + splits - 1) / splits + 63) / 64 * 64;
+  p.nstage = 3;
+  const int smem_bytes = p.nstage * 2 * kBSlabBytes + 512;
+  const long long n_units = static_cast<long long>(p.ta) * p.tb * splits;
+  const unsigned grid = static_cast<unsigned>(n_units < G ? n_units : G);
+  static bool done[FK_MAX_DEVICES];
+  const int r2 = set_smem_attr(gemm_tn_kernel, done[fk_device_ordinal()], kGemmSmemLimit);
+  if (r2 != FK_OK) return r2;
+  gemm_tn_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+  FK_CHECK_LAUNCH();
+  const long long n4 = static_cast<long long>(Na) * Nb / 4;
+  gemm_tn_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(ws, out, n4, splits);
+  FK_CHECK_LAUNCH();
+  fk_count_launch(2);
+  return FK_OK;
+}

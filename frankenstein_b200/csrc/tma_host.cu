@@ -41,6 +41,20 @@ int make_tmap_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint
   return make_tmap_bf16(map, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {ld * 2};
+  const uint32_t box[2] = {64, box_rows};
+  return make_tmap_bf16(map, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  const uint64_t dims[3] = {64, rows, cols / 64};
+  const uint64_t strides[2] = {ld * 2, 128};
+  const uint32_t box[3] = {64, 64, 4};
+  return make_tmap_bf16(map, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int make_tmap_heads_sw64(CUtensorMap* map, const void* base, int B, int S, int H, long long batch_stride,
                          long long token_stride, uint32_t box_rows) {
   const uint64_t dims[4] = {32, static_cast<uint64_t>(H), static_cast<uint64_t>(S), static_cast<uint64_t>(B)};

@@ -13,6 +13,14 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 // bf16 row-major [rows, cols] matrix, box = 64 columns x box_rows rows, 128-byte swizzle.
 int make_tmap_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
+// bf16 row-major [rows, cols] with leading dimension ld (elements): box = 64 columns x box_rows rows, 128-byte swizzle;
+// out-of-range rows / columns are filled with zeros.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+// The same matrix as an MN-major operand source: dims (64 columns of a chunk, rows, chunk index), box = 64 x 64 rows x 4
+// chunks -> shared memory [chunk][row][64 elements] (8 KB per chunk), 128-byte swizzle.  cols % 64 == 0.
+int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);
+
 // bf16 [B][S][H][32] with token / batch strides (elements): box = one head's 32 columns x box_rows tokens,
 // 64-byte swizzle.  Coordinates: (0, head, token, batch).
 int make_tmap_heads_sw64(CUtensorMap* map, const void* base, int B, int S, int H, long long batch_stride,

@@ -201,6 +201,7 @@ class LabelMask:
         require_cuda(qid)
         self.qid = qid.to(torch.int32).contiguous()
         self.kid = self.qid if kid is None else kid.to(torch.int32).contiguous()
+        self._pairs = None
         self.qmin, self.qmax = self._ranges(self.qid)
         if self.kid is self.qid:
             self.kmin, self.kmax = self.qmin, self.qmax
@@ -230,6 +231,14 @@ class LabelMask:
         kid = torch.where(is_padded, big, 0).to(torch.int32)
         qid = torch.where(is_padded, -1, 0).to(torch.int32)
         return LabelMask(qid, kid)
+
+    def visible_pairs(self) -> torch.Tensor:
+        """number of (query, key) pairs the mask lets through, summed over the batch: a 0-dim device tensor (no host
+        sync) -- the algorithmic work of the attention kernels for the per-launch roofline figures of bench.py."""
+        if self._pairs is None:
+            k_sorted = torch.sort(self.kid, dim=1)[0]
+            self._pairs = torch.searchsorted(k_sorted, self.qid.contiguous(), right=True).sum(dtype=torch.float64)
+        return self._pairs
 
     def dense(self) -> torch.Tensor:
         """[B, 1, Sq, Sk] bool, True = attend (only for tests / the library-SDPA compatibility path)."""
@@ -271,8 +280,9 @@ _BWD_PROFILE = None     # diagnosis hook: (int64 counter tensor, mode) -> fk_att
 class _AttnQKVFn(torch.autograd.Function):
     @staticmethod
     @on_tensor_device
-    def forward(ctx, qkv, n_heads, rope, mask, scale):
-        """qkv: bf16 [B, S, 3*H*32] fresh output of the fused projection (q|k|v); RoPE is applied in place."""
+    def forward(ctx, qkv, n_heads, rope, mask, scale, rope_applied=False):
+        """qkv: bf16 [B, S, 3*H*32] fresh output of the fused projection (q|k|v); RoPE is applied in place unless the
+        projection's epilogue already did it (rope_applied: the backward still rotates dq / dk back)."""
         require_cuda(qkv)
         require_device()
         if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous():
@@ -282,7 +292,8 @@ class _AttnQKVFn(torch.autograd.Function):
         hd = W // (3 * H)
         v5 = qkv.view(B, S, 3, H, hd)
         q, k, v = v5[:, :, 0], v5[:, :, 1], v5[:, :, 2]
-        if rope is not None:
+        rotate_here = rope is not None and not rope_applied
+        if rotate_here:
             _rope_inplace(q, rope, False)
             _rope_inplace(k, rope, False)
         out = torch.empty(B, S, H * hd, device=qkv.device, dtype=torch.bfloat16)
@@ -291,22 +302,27 @@ class _AttnQKVFn(torch.autograd.Function):
         m = mask
         margs = (ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0, ptr(m.qmax) if m else 0,
                  ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0, float(scale))
+        # algorithmic flops of one score-shaped matmul over the visible pairs (only evaluated while bench.py's timer is on)
+        qk = 0.0
+        if _lib.TIMER.enabled:
+            qk = (m.visible_pairs() if m else float(B) * S * S) * (2.0 * H * hd)
+        ctx.qk_flops = qk
         if ATTN_FWD_IMPL == "legacy":
-            with timed("attn_fwd"):
+            with timed("attn_fwd", 2 * qk):
                 check(lib().fk_attn_forward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, S, hd,
                                             q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                                             out.stride(0), out.stride(1), *margs, stream()), "fk_attn_forward")
         else:
-            with timed("attn_fwd"):
+            with timed("attn_fwd", 2 * qk):
                 check(lib().fk_attn_forward_tc(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, H, S, hd,
                                                q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                                                out.stride(0), out.stride(1), *margs, counters(_lib.CTR_ATTN_FWD), stream()),
                       "fk_attn_forward_tc")
-        if rope is not None:
+        if rotate_here:
             ctx.mark_dirty(qkv)          # q and k were rotated in place: autograd's version counter must see the write
         ctx.save_for_backward(qkv, out, lse)
         ctx.rope, ctx.mask, ctx.scale, ctx.H = rope, mask, scale, H
-        return out, (qkv if rope is not None else None)
+        return out, (qkv if rotate_here else None)
 
     @staticmethod
     @on_tensor_device
@@ -326,8 +342,10 @@ class _AttnQKVFn(torch.autograd.Function):
         common = (ptr(m.qid) if m else 0, ptr(m.kid) if m else 0, ptr(m.qmin) if m else 0, ptr(m.qmax) if m else 0,
                   ptr(m.kmin) if m else 0, ptr(m.kmax) if m else 0, float(ctx.scale))
 
+        work = {"attn_delta": 0.0, "attn_bwd_dkv": 4 * ctx.qk_flops, "attn_bwd_dq": 1 * ctx.qk_flops}
+
         def legacy(name, part):
-            with timed(name):
+            with timed(name, work[name]):
                 check(lib().fk_attn_backward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk),
                                              ptr(dv), B, H, S, S, hd, q.stride(0), q.stride(1), k.stride(0), k.stride(1),
                                              v.stride(0), v.stride(1), out.stride(0), out.stride(1), d_o.stride(0), d_o.stride(1),
@@ -363,7 +381,7 @@ class _AttnQKVFn(torch.autograd.Function):
                         q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                         d4.stride(0), d4.stride(1), dq.stride(0), dq.stride(1), dk.stride(0),
                         dk.stride(1), dv.stride(0), dv.stride(1), *common, *rope_args, part, counters(_lib.CTR_ATTN_BWD))
-                with timed(name):
+                with timed(name, work[name]):
                     if _BWD_PROFILE is not None:
                         check(lib().fk_attn_backward_tc_profile(*args, ptr(_BWD_PROFILE[0]), int(_BWD_PROFILE[1]), stream()),
                               "fk_attn_backward_tc_profile")
@@ -373,15 +391,15 @@ class _AttnQKVFn(torch.autograd.Function):
         if ctx.rope is not None and not rope_done:
             _rope_inplace(dq, ctx.rope, True)
             _rope_inplace(dk, ctx.rope, True)
-        return dqkv, None, None, None, None
+        return dqkv, None, None, None, None, None
 
 
 def attention_qkv(qkv, n_heads: int, rope: Optional[RopeSpec] = None, mask: Optional[LabelMask] = None,
-                  scale: Optional[float] = None):
+                  scale: Optional[float] = None, rope_applied: bool = False):
     """softmax(q k^T * scale + mask) v over the fused QKV buffer -> [B, S, H*32] bf16."""
     hd = qkv.shape[-1] // (3 * n_heads)
     if hd != 32:
         raise FkError("the attention kernel is built for head_dim 32")
     if scale is None:
         scale = hd ** -0.5
-    return _AttnQKVFn.apply(qkv, n_heads, rope, mask, scale)[0]
+    return _AttnQKVFn.apply(qkv, n_heads, rope, mask, scale, rope_applied)[0]

@@ -200,6 +200,30 @@ int fk_add_norm_backward(const float* x_new, const void* g_y, int g_dtype, const
                          const float* mean, const float* rstd, float* dx, void* dx_bf16, float* dw_part, float* db_part,
                          long long M, int D, int rms, void* stream);
 
+/* ---- dense bf16 GEMMs with fused epilogues (gemm.cu; tcgen05 / TMEM / TMA) ----------------------- */
+/* C[M,N] (bf16) = A[M,K] (bf16, row-major, lda) x B[N,K]^T (bf16, row-major, ldb = an nn.Linear weight), fp32 accumulate.
+ * Replaces the nn.Linear calls of models/brainformer.py:119-124 (MLP), :141-145,171 (qw/kw/vw fused, project), :285 (emb)
+ * and, on transposed weight copies, their input gradients.  K % 8 == 0, N % 32 == 0.  K <= 512 runs the A-resident
+ * kernel (all epilogues); longer K the streaming kernel (epilogue 0 only).  epilogue:
+ *   0  C = A B^T (+ bias[N], nullable)
+ *   1  apply_rope (brainformer.py:70-91) on columns [0, rope_cols) of C (heads of 32 columns; q | k of the fused
+ *      projection): rope_table [rope_len][16][2] (cos, sin), position of row m = rope_pos ? rope_pos[m]
+ *      : (m % rope_S) + rope_offset
+ *   2  SwiGLU forward: B = w1 / w3 interleaved in blocks of 128 rows ([w1[0:128]; w3[0:128]; w1[128:256]; ...], N = 2 x
+ *      hidden); writes the fused projection C = h13 [M, N] and C2 = gated [M, N/2] = silu(h1) * h3 (brainformer.py:123-124)
+ *   3  SwiGLU backward: A = d out, B = w2^T ([hidden, dim]), N = hidden; the accumulator d gated is combined with
+ *      aux = h13 [M, 2N] (interleaved as above) into C2 = dh13 [M, 2N]; C is not written. */
+int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, long long M, int N,
+               int K, const float* bias, int epilogue, void* C2, long long ldc2, const void* aux, long long ld_aux,
+               const float* rope_table, int rope_len, const int* rope_pos, int rope_offset, int rope_cols, int rope_S,
+               void* stream);
+/* out[Na,Nb] (fp32) = A[M,Na]^T x B[M,Nb] (bf16, row-major): the weight gradient dW = dY^T X of an nn.Linear.  The M rows
+ * are cut into `splits` = fk_gemm_tn_splits(M, Na, Nb, 0) ranges whose partial sums go to ws (fp32 [splits, Na, Nb]) and
+ * are added in a fixed order (bit-reproducible).  Na % 64 == 0, Nb % 64 == 0.  max_ctas <= 0: the SM count. */
+int fk_gemm_tn_splits(long long M, int Na, int Nb, int max_ctas);
+int fk_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* out, long long M, int Na, int Nb,
+               float* ws, int splits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
