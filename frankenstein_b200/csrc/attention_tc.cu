@@ -89,7 +89,8 @@ struct TcSmem {
 
 // FK_ATTN_EXP (diagnosis builds only, results are WRONG): 1 = no MUFU, 2 = no TMEM operand stores, 3 = no stats LDS,
 // 4 = no math at all between the TMEM loads and stores, 5 = no delta subtraction (and no delta LDS),
-// 6 = neither delta nor lse (P = ex2(S * c)).
+// 6 = neither delta nor lse (P = ex2(S * c)), 7 = 6 + no statistics staging / named barrier and no scale multiply
+// (P = ex2(S)): the upper bound of folding lse, delta and the softmax scale into the score MMAs.
 #ifndef FK_ATTN_EXP
 #define FK_ATTN_EXP 0
 #endif
@@ -495,6 +496,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       float* s_lse = stats_base + (n & 1) * 192;
       float* s_delta = s_lse + 64;
       int* s_id = reinterpret_cast<int*>(s_lse + 128);
+#if FK_ATTN_EXP != 7
       if (MODE == MODE_DKV) {
         if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else { s_delta[tid - 64] = pre_f; }
       } else if (tid < 64) {
@@ -504,6 +506,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       named_bar_sync(1 + g, 128);
       if (kFull) w_bar += clock64() - tb0;
       prefetch(j + kNG);
+#endif
       wait_acc<kProf>(&sdp_full[g], n & 1, w_full);
       if (prof_me && j == j0) prof[3] = clock64() - t_start;
       if (kFull && trace && q4 == 0 && lane == 0 && j < 128) trace[4 * 128 + j] = clock64();
@@ -536,7 +539,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
           float lse8[8], dl8[8];
-          if (MODE == MODE_DKV && FK_ATTN_EXP != 3) {
+          if (MODE == MODE_DKV && FK_ATTN_EXP != 3 && FK_ATTN_EXP != 7) {
             const float4 l0 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8);
             const float4 l1 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8 + 4);
             const float4 d0 = *reinterpret_cast<const float4*>(s_delta + i * 16 + g8 * 8);
@@ -558,11 +561,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
 #if FK_ATTN_EXP == 6
             const float p0 = fast_ex2(__uint_as_float(sv[cur][i0]) * p.scale_log2);
             const float p1 = fast_ex2(__uint_as_float(sv[cur][i0 + 1]) * p.scale_log2);
+#elif FK_ATTN_EXP == 7
+            const float p0 = fast_ex2(__uint_as_float(sv[cur][i0]));
+            const float p1 = fast_ex2(__uint_as_float(sv[cur][i0 + 1]));
 #else
             const float p0 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0]), p.scale_log2, -lse8[e2 * 2]));
             const float p1 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0 + 1]), p.scale_log2, -lse8[e2 * 2 + 1]));
 #endif
-#if FK_ATTN_EXP == 5 || FK_ATTN_EXP == 6
+#if FK_ATTN_EXP == 5 || FK_ATTN_EXP == 6 || FK_ATTN_EXP == 7
             const float s0 = p0 * __uint_as_float(dv[cur][i0]);           // what folding delta into the dP MMA would leave
             const float s1 = p1 * __uint_as_float(dv[cur][i0 + 1]);
 #else

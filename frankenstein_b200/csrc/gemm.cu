@@ -22,6 +22,9 @@
 //
 // L2 -> SM traffic bounds these shapes as much as the tensor pipe does (K is only 512..4096): a 128-row resident block or
 // a 256 x 256 streamed tile needs one operand byte per 128 flops, about what the L2 fabric delivers at the bf16 peak.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "fk_b200.h"
 #include "tma_host.cuh"
@@ -48,6 +51,7 @@ struct GemmParams {
   int rope_len, rope_offset, rope_cols, rope_S;
   long long M;
   int N, K, nslab, ntile, nstage;
+  int dbg;                   // diagnosis (FK_GEMM_DBG): bit 0 = the epilogue releases its accumulator without reading / storing it
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -109,21 +113,254 @@ __device__ __forceinline__ void to_f32(const uint32_t (&r)[32], float (&v)[32]) 
 }
 __device__ __forceinline__ float sigmoidf_fast(float x) { return 1.f / (1.f + __expf(-x)); }
 
-struct GemmSmem {
-  uint64_t* bars;
-};
+// ---- coalesced epilogue I/O through a per-warp 2 KB staging tile (16 rows x 128 bytes, two passes per 32 rows) ----------
+// An accumulator row belongs to one thread (TMEM lane = row), so direct stores are 32 rows x 16 bytes per instruction:
+// 32 half-used sectors -- measured, that store path (not the tensor pipe, not L2 reads) paced the A-resident kernel at
+// ~1.9 TB/s of output.  Through the staging tile every global access is a full 128-byte line (8 lanes per row, 4 rows per
+// instruction).  16-byte pieces are XOR-swizzled with (row & 7): row-wise and line-wise patterns are both conflict free.
+//
+// warp_store_32x64: lane l holds columns 0..63 of row (row0 + l) as 32 packed bf16 pairs.
+__device__ __forceinline__ void warp_store_32x64(uint8_t* stg, int lane, const uint32_t (&w)[32], __nv_bfloat16* dst, long long ld,
+                                                 long long row0, long long M, int dbg) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    __syncwarp();                                   // the previous pass's readers are done with the tile
+    if ((lane >> 4) == half) {
+      const int r = lane & 15;
+#pragma unroll
+      for (int pc = 0; pc < 8; ++pc)
+        *reinterpret_cast<uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4)) = make_uint4(w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = j * 4 + (lane >> 3), pc = lane & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4));
+      const long long grow = row0 + half * 16 + r;
+      if (dbg & 2) { if (v.x == 0x12345678u && v.y == 0x9abcdef0u) *reinterpret_cast<uint4*>(dst) = v; continue; }   // diagnosis: no global stores
+      if (grow < M) *reinterpret_cast<uint4*>(dst + grow * ld + pc * 8) = v;
+    }
+  }
+}
+// Same through the TMA store engine (one bulk tensor store of the 16 x 128-byte tile per pass instead of 4 STG.128 per lane):
+// the tile layout above IS the 128-byte TMA swizzle; rows / columns outside the tensor are clipped by the hardware.
+__device__ __forceinline__ void warp_store_32x64_tma(uint8_t* stg0, int lane, const uint32_t (&w)[32], const CUtensorMap* tm,
+                                                     int col, long long row0) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint8_t* stg = stg0;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous store has read the tile
+    __syncwarp();
+    if ((lane >> 4) == half) {
+      const int r = lane & 15;
+#pragma unroll
+      for (int pc = 0; pc < 8; ++pc)
+        *reinterpret_cast<uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4)) = make_uint4(w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
+    }
+    fence_proxy_async();                            // generic-proxy writes -> visible to the async proxy (TMA)
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                   ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(static_cast<int>(row0) + half * 16), "r"(smem_u32(stg))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+}
+// warp_load_32x64: issue the global loads in the full-line pattern (early), then pass them through the tile so that lane l
+// ends up with columns 0..63 of row (row0 + l).
+__device__ __forceinline__ void warp_load_issue_32x64(const __nv_bfloat16* src, long long ld, long long row0, long long M, int lane,
+                                                      uint4 (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long grow = row0 + j * 4 + (lane >> 3);
+    v[j] = (grow < M) ? *reinterpret_cast<const uint4*>(src + grow * ld + (lane & 7) * 8) : make_uint4(0, 0, 0, 0);
+  }
+}
+__device__ __forceinline__ void warp_load_finish_32x64(uint8_t* stg, int lane, const uint4 (&v)[8], uint32_t (&w)[32]) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // a TMA store may still be reading the tile
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = j * 4 + (lane >> 3), pc = lane & 7;
+      *reinterpret_cast<uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4)) = v[half * 4 + j];
+    }
+    __syncwarp();
+    if ((lane >> 4) == half) {
+      const int r = lane & 15;
+#pragma unroll
+      for (int pc = 0; pc < 8; ++pc) {
+        const uint4 t = *reinterpret_cast<const uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4));
+        w[4 * pc] = t.x; w[4 * pc + 1] = t.y; w[4 * pc + 2] = t.z; w[4 * pc + 3] = t.w;
+      }
+    }
+  }
+}
+
+// One 128 x 256 accumulator tile of the A-resident kernels: this warp's 32 rows (TMEM lane quarter) x 128 columns (half ch).
+template <int EPI, class Release>
+__device__ __forceinline__ void res_epilogue_tile(const GemmParams& p, const CUtensorMap& tm_c, const CUtensorMap& tm_c2, uint8_t* stg,
+                                                  int lane, int ch, uint32_t taddr, int n0, long long row0, const float2 (&cs)[16],
+                                                  uint64_t* full_bar, uint32_t full_parity, Release release) {
+    const long long row = row0 + lane;
+    (void)row;
+    if (p.dbg & 1) {
+      mbar_wait(full_bar, full_parity);
+      tc_fence_after();
+      release();
+      return;
+    }
+    if (EPI == EPI_STORE || EPI == EPI_ROPE) {
+      mbar_wait(full_bar, full_parity);
+      tc_fence_after();
+#pragma unroll
+      for (int dc = 0; dc < 2; ++dc) {               // two 64-column halves of this warp's 128 columns
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr + ch * 128 + dc * 64, r0);
+        tmem_ld32(taddr + ch * 128 + dc * 64 + 32, r1);
+        tmem_wait_ld32(r0);
+        tmem_wait_ld32(r1);
+        if (dc == 1) release();
+        const int col = n0 + ch * 128 + dc * 64;
+        uint32_t w[32];
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          float v[32];
+          if (hc == 0) to_f32(r0, v); else to_f32(r1, v);
+          if (EPI == EPI_ROPE) {
+            if (col + hc * 32 < p.rope_cols) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float x0 = v[2 * i], x1 = v[2 * i + 1];
+                v[2 * i] = x0 * cs[i].x - x1 * cs[i].y;
+                v[2 * i + 1] = x0 * cs[i].y + x1 * cs[i].x;
+              }
+            }
+          } else if (p.bias != nullptr && col + hc * 32 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + hc * 32) + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[hc * 16 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+        }
+        if (col < p.N) {
+          if (p.dbg & 4) warp_store_32x64(stg, lane, w, p.C + col, p.ldc, row0, p.M, p.dbg);     // diagnosis: LSU stores (N % 64 == 0)
+          else warp_store_32x64_tma(stg, lane, w, &tm_c, col, row0);
+        }
+      }
+    } else if (EPI == EPI_SWIGLU) {
+      // tile columns: [0,128) = w1 block, [128,256) = w3 block of the same 128 hidden units (weights interleaved by the
+      // host in blocks of 128).  This warp: hidden units ch*64 .. ch*64+63 of the block.
+      mbar_wait(full_bar, full_parity);
+      tc_fence_after();
+      uint32_t wa[32], wb[32];
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr + ch * 64, r0);
+        tmem_ld32(taddr + ch * 64 + 32, r1);
+        tmem_wait_ld32(r0);
+        tmem_wait_ld32(r1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          wa[i] = pack_bf16(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+          wa[16 + i] = pack_bf16(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+        }
+        tmem_ld32(taddr + 128 + ch * 64, r0);
+        tmem_ld32(taddr + 128 + ch * 64 + 32, r1);
+        tmem_wait_ld32(r0);
+        tmem_wait_ld32(r1);
+        release();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          wb[i] = pack_bf16(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+          wb[16 + i] = pack_bf16(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+        }
+      }
+      const int ca = n0 + ch * 64;                            // column of the w1 part inside h13
+      if (ca < p.N) {
+        warp_store_32x64_tma(stg, lane, wa, &tm_c, ca, row0);
+        warp_store_32x64_tma(stg, lane, wb, &tm_c, ca + 128, row0);
+        // the saved h13 is bf16: gate from the ROUNDED values, so that backward (which reads h13) sees the same function
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float a0 = bf16_lo(wa[i]), a1 = bf16_hi(wa[i]), b0 = bf16_lo(wb[i]), b1 = bf16_hi(wb[i]);
+          wa[i] = pack_bf16(a0 * sigmoidf_fast(a0) * b0, a1 * sigmoidf_fast(a1) * b1);
+        }
+        warp_store_32x64_tma(stg, lane, wa, &tm_c2, (n0 >> 1) + ch * 64, row0);
+      }
+    } else {   // EPI_SWIGLU_BWD: accumulator = d gated [M, N]; this warp: hidden block n0/128 + ch (128 units)
+      const long long o0 = 2ll * (n0 + ch * 128);             // column of h1 of the block inside the interleaved h13 / dh13
+      const bool ok = n0 + ch * 128 < p.N;
+      uint4 g1[8], g3[8];
+      if (ok) {                                                // h1 / h3 of the first 64 units: in flight while the MMAs finish
+        warp_load_issue_32x64(p.aux + o0, p.ld_aux, row0, p.M, lane, g1);
+        warp_load_issue_32x64(p.aux + o0 + 128, p.ld_aux, row0, p.M, lane, g3);
+      }
+      mbar_wait(full_bar, full_parity);
+      tc_fence_after();
+#pragma unroll
+      for (int dc = 0; dc < 2; ++dc) {
+        uint32_t w1[32], w3[32];
+        if (ok) {
+          warp_load_finish_32x64(stg, lane, g1, w1);
+          warp_load_finish_32x64(stg, lane, g3, w3);
+        }
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          uint32_t r[32];
+          tmem_ld32(taddr + ch * 128 + dc * 64 + hc * 32, r);
+          tmem_wait_ld32(r);
+          if (dc == 1 && hc == 1) release();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float o1[2], o3[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t x1 = w1[hc * 16 + i], x3 = w3[hc * 16 + i];
+              const float h1 = hh ? bf16_hi(x1) : bf16_lo(x1), h3 = hh ? bf16_hi(x3) : bf16_lo(x3);
+              const float dg = __uint_as_float(r[2 * i + hh]);
+              const float sg = sigmoidf_fast(h1);
+              const float silu = h1 * sg;
+              o1[hh] = dg * h3 * (sg + silu * (1.f - sg));     // d silu(x)/dx = s + x s (1 - s)
+              o3[hh] = dg * silu;
+            }
+            w1[hc * 16 + i] = pack_bf16(o1[0], o1[1]);          // in place: d h1 over h1, d h3 over h3
+            w3[hc * 16 + i] = pack_bf16(o3[0], o3[1]);
+          }
+        }
+        if (ok && dc == 0) {                                   // the second 64 units' h1 / h3
+          warp_load_issue_32x64(p.aux + o0 + 64, p.ld_aux, row0, p.M, lane, g1);
+          warp_load_issue_32x64(p.aux + o0 + 64 + 128, p.ld_aux, row0, p.M, lane, g3);
+        }
+        if (ok) {
+          warp_store_32x64_tma(stg, lane, w1, &tm_c2, static_cast<int>(o0) + dc * 64, row0);
+          warp_store_32x64_tma(stg, lane, w3, &tm_c2, static_cast<int>(o0) + dc * 64 + 128, row0);
+        }
+      }
+    }
+}
 
 // ================================================================================================
 // A-resident kernel (K <= 512)
 // ================================================================================================
+constexpr int kBStageBytes = 256 * 64;     // 256 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
+constexpr int kStageTileBytes = 2048;      // per epilogue warp: 16 rows x 128 bytes
+
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
+gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_c2, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* As = smem;                                        // nslab x 16 KB
-  uint8_t* Bs = As + p.nslab * kASlabBytes;                  // nstage x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + p.nstage * kBSlabBytes);
+  uint8_t* As = smem;                                        // nslab x 16 KB (64-wide k-slabs, SWIZZLE_128B)
+  uint8_t* Bs = As + p.nslab * kASlabBytes;                  // nstage x 16 KB (32-wide k-slabs, SWIZZLE_64B)
+  uint8_t* Stg = Bs + p.nstage * kBStageBytes;               // 8 x 2 KB epilogue staging tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Stg + 8 * kStageTileBytes);
   uint64_t* a_full = bars;            // [8]
   uint64_t* a_empty = bars + 8;       // [8]
   uint64_t* b_full = bars + 16;       // [8]
@@ -133,7 +370,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_c2); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 8; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
@@ -149,16 +386,18 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_blocks = static_cast<int>((p.M + 127) / 128);
+  const int nkb = (p.K + 31) / 32;          // 32-wide k-slabs of B; A slab of k-slab j = j / 2
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     int stage = 0;
-    uint32_t phase = 0, it = 0;
+    uint32_t phase = 0, it = 0, nload = 0;
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
       for (int t = 0; t < p.ntile; ++t) {
-        for (int ks = 0; ks < p.nslab; ++ks) {
-          if (t == 0) {
-            // A slab ks of this block: free once the last tile of the previous block has consumed it
+        for (int j = 0; j < nkb; ++j) {
+          if (t == 0 && (j & 1) == 0) {
+            // A slab j/2 of this block: free once the last tile of the previous block has consumed it
+            const int ks = j >> 1;
             mbar_wait(&a_empty[ks], (it & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&a_full[ks], kASlabBytes);
@@ -166,10 +405,12 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
             __syncwarp();
           }
+          if ((p.dbg & 32) && nload >= static_cast<uint32_t>(p.nstage)) continue;     // diagnosis: B ring filled once, never reloaded
+          ++nload;
           mbar_wait(&b_empty[stage], phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&b_full[stage], kBSlabBytes);
-            tma_load_2d(Bs + stage * kBSlabBytes, &tm_b, &b_full[stage], ks * 64, t * 256);
+            mbar_expect_tx(&b_full[stage], kBStageBytes);
+            tma_load_2d(Bs + stage * kBStageBytes, &tm_b, &b_full[stage], j * 32, t * 256);
           }
           __syncwarp();
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -182,24 +423,40 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t as_addr = smem_u32(As), bs_addr = smem_u32(Bs);
     int stage = 0;
-    uint32_t phase = 0, it = 0, tc = 0;
+    uint32_t phase = 0, it = 0, tc = 0, nuse = 0;
+    long long w_te = 0, w_a = 0, w_b = 0;                   // diagnosis (FK_GEMM_DBG & 16): cycles blocked per barrier kind
+    const bool prof = (p.dbg & 16) != 0;
+    const long long t_begin = prof ? clock64() : 0;
+    auto timed_wait = [&](uint64_t* bar, uint32_t ph, long long& acc) {
+      if (prof) {
+        if (mbar_test_wait(bar, ph)) return;
+        const long long t0 = clock64();
+        mbar_wait(bar, ph);
+        acc += clock64() - t0;
+      } else {
+        mbar_wait(bar, ph);
+      }
+    };
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
       for (int t = 0; t < p.ntile; ++t, ++tc) {
         const uint32_t as = tc & 1;
-        mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
+        timed_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1, w_te);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + as * 256;
-        for (int ks = 0; ks < p.nslab; ++ks) {
-          if (t == 0) mbar_wait(&a_full[ks], it & 1);
-          mbar_wait(&b_full[stage], phase);
+        for (int j = 0; j < nkb; ++j) {
+          const int ks = j >> 1;
+          if (t == 0 && (j & 1) == 0) timed_wait(&a_full[ks], it & 1, w_a);
+          if (!(p.dbg & 32) || nuse < static_cast<uint32_t>(p.nstage)) timed_wait(&b_full[stage], phase, w_b);
+          ++nuse;
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(as_addr + ks * kASlabBytes);
-          const uint64_t bdesc = umma_desc_sw128(bs_addr + stage * kBSlabBytes);
+          // A: 64-byte half (j & 1) of the 128-byte swizzled rows of slab ks; a K step of 16 elements = +32 B = +2
+          const uint64_t adesc = umma_desc_sw128(as_addr + ks * kASlabBytes) + 4 * (j & 1);
+          const uint64_t bdesc = umma_desc_sw64(bs_addr + stage * kBStageBytes);
           if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (ks | kk) != 0);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, j != 0);
+            umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
             umma_commit(&b_empty[stage]);
-            if (t == p.ntile - 1) umma_commit(&a_empty[ks]);
+            if (t == p.ntile - 1 && ((j & 1) == 1 || j == nkb - 1)) umma_commit(&a_empty[ks]);
           }
           __syncwarp();
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -208,116 +465,40 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         __syncwarp();
       }
     }
+    if (prof && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+      printf("gemm_res<%d> cta %d: issuer total %lld cycles, %u tiles; blocked on tmem_empty %lld, a_full %lld, b_full %lld\n", EPI,
+             static_cast<int>(blockIdx.x), clock64() - t_begin, tc, w_te, w_a, w_b);
   } else if (warp >= 4) {
     // ================================ epilogue ================================
     const int e = warp - 4;
     const int q = warp & 3;          // TMEM lane quarter this warp may read
     const int ch = e >> 2;           // column half of the 256-column tile
+    uint8_t* stg = Stg + e * kStageTileBytes;
     uint32_t tc = 0;
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-      const long long row = static_cast<long long>(blk) * 128 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const long long row0 = ((p.dbg & 8) ? 0ll : static_cast<long long>(blk) * 128) + q * 32;     // first row of this warp (dbg 8: every block writes rows 0..127 -> L2 only)
+      const long long row = row0 + lane;
       float2 cs[16];
       if (EPI == EPI_ROPE) {
         int ps = 0;
-        if (row_ok) ps = p.rope_pos ? p.rope_pos[row] : static_cast<int>(row % p.rope_S) + p.rope_offset;
+        if (row < p.M) ps = p.rope_pos ? p.rope_pos[row] : static_cast<int>(row % p.rope_S) + p.rope_offset;
         ps = min(max(ps, 0), p.rope_len - 1);
 #pragma unroll
         for (int i = 0; i < 16; ++i) cs[i] = __ldg(p.rope_table + static_cast<long long>(ps) * 16 + i);
       }
       for (int t = 0; t < p.ntile; ++t, ++tc) {
         const uint32_t as = tc & 1;
-        mbar_wait(&tmem_full[as], (tc >> 1) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
         const int n0 = t * 256;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
         auto release = [&]() {           // every TMEM read of this accumulator stage by this warp has completed
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[as]);
         };
-        if (EPI == EPI_STORE || EPI == EPI_ROPE) {
-          uint32_t r[2][32];
-          tmem_ld32(taddr + ch * 128, r[0]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            tmem_wait_ld32(r[c & 1]);
-            if (c < 3) tmem_ld32(taddr + ch * 128 + (c + 1) * 32, r[(c + 1) & 1]);
-            else release();
-            const int col = n0 + ch * 128 + c * 32;
-            float v[32];
-            to_f32(r[c & 1], v);
-            if (EPI == EPI_ROPE) {
-              if (col < p.rope_cols) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float x0 = v[2 * i], x1 = v[2 * i + 1];
-                  v[2 * i] = x0 * cs[i].x - x1 * cs[i].y;
-                  v[2 * i + 1] = x0 * cs[i].y + x1 * cs[i].x;
-                }
-              }
-            } else if (p.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += (col + i < p.N) ? __ldg(p.bias + col + i) : 0.f;
-            }
-            if (row_ok && col < p.N) store32_bf16(p.C + row * p.ldc + col, v);      // (N % 32 == 0 is required)
-          }
-        } else if (EPI == EPI_SWIGLU) {
-          // tile columns: [0,128) = w1 block, [128,256) = w3 block of the same 128 hidden units (weights interleaved by the
-          // host in blocks of 128).  This warp: hidden units ch*64 .. ch*64+63 of the block.
-          uint32_t ra[32], rb[32];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            tmem_ld32(taddr + ch * 64 + c * 32, ra);
-            tmem_ld32(taddr + 128 + ch * 64 + c * 32, rb);
-            tmem_wait_ld32(ra);
-            tmem_wait_ld32(rb);
-            if (c == 1) release();
-            float a[32], b[32], g[32];
-            to_f32(ra, a);
-            to_f32(rb, b);
-            const int ca = n0 + ch * 64 + c * 32;                 // column of the w1 part inside h13
-            if (row_ok && ca < p.N) {
-              // the saved h13 is bf16: gate from the ROUNDED values, so that backward (which reads h13) sees the same function
-              store32_bf16(p.C + row * p.ldc + ca, a);
-              store32_bf16(p.C + row * p.ldc + ca + 128, b);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float h1 = __bfloat162float(__float2bfloat16_rn(a[i])), h3 = __bfloat162float(__float2bfloat16_rn(b[i]));
-                g[i] = h1 * sigmoidf_fast(h1) * h3;
-              }
-              store32_bf16(p.C2 + row * p.ldc2 + (n0 >> 1) + ch * 64 + c * 32, g);
-            }
-          }
-        } else {   // EPI_SWIGLU_BWD: accumulator = d gated [M, N]; this warp: hidden block n0/128 + ch (128 units)
-          uint32_t r[2][32];
-          tmem_ld32(taddr + ch * 128, r[0]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            tmem_wait_ld32(r[c & 1]);
-            if (c < 3) tmem_ld32(taddr + ch * 128 + (c + 1) * 32, r[(c + 1) & 1]);
-            else release();
-            const int col = n0 + ch * 128 + c * 32;               // hidden unit
-            if (row_ok && col < p.N) {
-              const long long o = 2ll * (n0 + ch * 128) + c * 32;    // column of h1 inside the interleaved h13 / dh13
-              float dg[32], h1[32], h3[32], d1[32], d3[32];
-              to_f32(r[c & 1], dg);
-              load32_bf16(p.aux + row * p.ld_aux + o, h1);
-              load32_bf16(p.aux + row * p.ld_aux + o + 128, h3);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float s = sigmoidf_fast(h1[i]);
-                const float silu = h1[i] * s;
-                d1[i] = dg[i] * h3[i] * (s + silu * (1.f - s));     // d silu(x)/dx = s + x s (1 - s)
-                d3[i] = dg[i] * silu;
-              }
-              store32_bf16(p.C2 + row * p.ldc2 + o, d1);
-              store32_bf16(p.C2 + row * p.ldc2 + o + 128, d3);
-            }
-          }
-        }
+        res_epilogue_tile<EPI>(p, tm_c, tm_c2, stg, lane, ch, taddr, n0, row0, cs, &tmem_full[as], (tc >> 1) & 1, release);
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all bulk stores of this warp have completed
   }
 
   tc_fence_before();
@@ -633,6 +814,11 @@ FK_API int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb
   p.rope_table = reinterpret_cast<const float2*>(rope_table); p.rope_pos = rope_pos; p.rope_len = rope_len;
   p.rope_offset = rope_offset; p.rope_cols = rope_cols; p.rope_S = rope_S;
   p.M = M; p.N = N; p.K = K;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("FK_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
   p.nslab = (K + 63) / 64;
   p.ntile = (N + 255) / 256;
   if (epilogue == EPI_STORE || epilogue == EPI_ROPE || epilogue == EPI_SWIGLU)
@@ -654,12 +840,19 @@ FK_API int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb
   const int G = fk_sm_count();
   if (K <= 512) {
     int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 128);
-    rc |= make_tmap_bf16_2d(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 256);
+    rc |= make_tmap_bf16_2d_sw64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 256);
     if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
-    int nstage = (kGemmSmemLimit - 512 - p.nslab * kASlabBytes) / kBSlabBytes;
-    if (nstage > 6) nstage = 6;
+    // outputs go through the TMA store engine: 16-row x 64-column boxes, 128-byte swizzle
+    CUtensorMap tc = ta, tc2 = ta;
+    if (C != nullptr) rc |= make_tmap_bf16_2d(&tc, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldc), 16);
+    if (C2 != nullptr)
+      rc |= make_tmap_bf16_2d(&tc2, C2, static_cast<uint64_t>(M), static_cast<uint64_t>(epilogue == EPI_SWIGLU ? N / 2 : 2 * N),
+                              static_cast<uint64_t>(ldc2), 16);
+    if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled(output) failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
+    int nstage = (kGemmSmemLimit - 512 - 8 * kStageTileBytes - p.nslab * kASlabBytes) / kBStageBytes;
+    if (nstage > 8) nstage = 8;
     p.nstage = nstage;
-    const int smem_bytes = p.nslab * kASlabBytes + nstage * kBSlabBytes + 512;
+    const int smem_bytes = p.nslab * kASlabBytes + nstage * kBStageBytes + 8 * kStageTileBytes + 512;
     const long long n_blocks = (M + 127) / 128;
     const unsigned grid = static_cast<unsigned>(n_blocks < G ? n_blocks : G);
     static bool done[4][FK_MAX_DEVICES];
@@ -667,19 +860,19 @@ FK_API int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb
     switch (epilogue) {
       case EPI_STORE:
         if ((r2 = set_smem_attr(gemm_res_kernel<EPI_STORE>, done[0][dev], kGemmSmemLimit)) != FK_OK) return r2;
-        gemm_res_kernel<EPI_STORE><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+        gemm_res_kernel<EPI_STORE><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, p);
         break;
       case EPI_ROPE:
         if ((r2 = set_smem_attr(gemm_res_kernel<EPI_ROPE>, done[1][dev], kGemmSmemLimit)) != FK_OK) return r2;
-        gemm_res_kernel<EPI_ROPE><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+        gemm_res_kernel<EPI_ROPE><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, p);
         break;
       case EPI_SWIGLU:
         if ((r2 = set_smem_attr(gemm_res_kernel<EPI_SWIGLU>, done[2][dev], kGemmSmemLimit)) != FK_OK) return r2;
-        gemm_res_kernel<EPI_SWIGLU><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+        gemm_res_kernel<EPI_SWIGLU><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, p);
         break;
       default:
         if ((r2 = set_smem_attr(gemm_res_kernel<EPI_SWIGLU_BWD>, done[3][dev], kGemmSmemLimit)) != FK_OK) return r2;
-        gemm_res_kernel<EPI_SWIGLU_BWD><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+        gemm_res_kernel<EPI_SWIGLU_BWD><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, p);
         break;
     }
   } else {

@@ -221,13 +221,17 @@ swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ h13, __nv_bfloat16* __restri
 
 __global__ void __launch_bounds__(256)
 swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ h13, const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ dh13,
-                  long long M, int H) {
+                  long long M, int H, int blk) {
+  // blk = H: columns [0,H) = w1 x, [H,2H) = w3 x; blk < H: blocks of blk hidden units stored as [w1 block | w3 block]
+  // (the layout the fused w1 | w3 GEMM of gemm.cu writes)
   const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (idx >= M * H) return;
   const long long row = idx / H;
-  const int c = static_cast<int>(idx % H);
+  const int cu = static_cast<int>(idx % H);
+  const int c = (cu / blk) * 2 * blk + (cu % blk);
+  const int H3 = blk;                       // distance from a unit's w1 column to its w3 column
   const uint4 a = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + c);
-  const uint4 b = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + H + c);
+  const uint4 b = *reinterpret_cast<const uint4*>(h13 + row * 2 * H + H3 + c);
   const uint4 g = *reinterpret_cast<const uint4*>(gy + idx);
   const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, gw[4] = {g.x, g.y, g.z, g.w};
   uint32_t da[4], db[4];
@@ -250,7 +254,7 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ h13, const __nv_bfloat16* __
     db[j] = *reinterpret_cast<uint32_t*>(&ob);
   }
   *reinterpret_cast<uint4*>(dh13 + row * 2 * H + c) = make_uint4(da[0], da[1], da[2], da[3]);
-  *reinterpret_cast<uint4*>(dh13 + row * 2 * H + H + c) = make_uint4(db[0], db[1], db[2], db[3]);
+  *reinterpret_cast<uint4*>(dh13 + row * 2 * H + H3 + c) = make_uint4(db[0], db[1], db[2], db[3]);
 }
 
 template <typename TIn, typename TOut>
@@ -340,7 +344,21 @@ FK_API int fk_swiglu_backward(const void* h13, const void* gy, void* dh13, long 
   FK_REQUIRE(h13 && gy && dh13 && M > 0 && H > 0 && H % 8 == 0, "fk_swiglu_backward: bad argument (H % 8 == 0)");
   const long long n = M * H / 8;
   swiglu_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(h13), static_cast<const __nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(dh13), M, H);
+      static_cast<const __nv_bfloat16*>(h13), static_cast<const __nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(dh13), M, H, H);
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
+  return FK_OK;
+}
+
+// Same on the block-interleaved projection the fused w1 | w3 GEMM (fk_gemm_nt, epilogue 2) writes: blocks of `block` hidden
+// units stored as [w1 block | w3 block]; gy [M, H] is in plain hidden-unit order.
+FK_API int fk_swiglu_backward_blocked(const void* h13, const void* gy, void* dh13, long long M, int H, int block, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(h13 && gy && dh13 && M > 0 && H > 0 && block > 0 && block % 8 == 0 && H % block == 0,
+             "fk_swiglu_backward_blocked: bad argument (block % 8 == 0, H % block == 0)");
+  const long long n = M * H / 8;
+  swiglu_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(h13), static_cast<const __nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(dh13), M, H, block);
   FK_CHECK_LAUNCH();
   fk_count_launch();
   return FK_OK;

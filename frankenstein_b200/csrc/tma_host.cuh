@@ -17,6 +17,9 @@ int make_tmap_bf16_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint
 // out-of-range rows / columns are filled with zeros.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
+// Same with 32-column boxes (64-byte rows) and the 64-byte swizzle.
+int make_tmap_bf16_2d_sw64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
 // The same matrix as an MN-major operand source: dims (64 columns of a chunk, rows, chunk index), box = 64 x 64 rows x 4
 // chunks -> shared memory [chunk][row][64 elements] (8 KB per chunk), 128-byte swizzle.  cols % 64 == 0.
 int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);

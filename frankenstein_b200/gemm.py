@@ -14,6 +14,7 @@ gradient, makes the transposed copy the NT kernel wants -- a few MB).  Weight gr
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -22,6 +23,9 @@ from ._lib import FkError, check, lib, on_tensor_device, ptr, require_cuda, requ
 
 BF16 = torch.bfloat16
 EPI_STORE, EPI_ROPE, EPI_SWIGLU, EPI_SWIGLU_BWD = 0, 1, 2, 3
+# backward of the SwiGLU MLP: "split" = d-gated GEMM + one streaming derivative pass (default, faster); "fused" = the
+# derivative in the GEMM epilogue (kept for A/B measurements and tested in tests/test_gemm_gpu.py)
+MLP_BWD = os.environ.get("FK_MLP_BWD", "split")
 
 
 def _as2d(x: torch.Tensor) -> torch.Tensor:
@@ -231,7 +235,19 @@ class _SwiGLUMLPFn(torch.autograd.Function):
     def backward(ctx, g):
         x2, h13, gated, w13, w2b = ctx.saved_tensors
         g2 = _as2d(g)
-        dh13 = gemm_nt(g2, w2b.t().contiguous(), None, EPI_SWIGLU_BWD, h13=h13, name="gemm_dgated_swiglu_bwd")
+        if MLP_BWD == "fused":
+            dh13 = gemm_nt(g2, w2b.t().contiguous(), None, EPI_SWIGLU_BWD, h13=h13, name="gemm_dgated_swiglu_bwd")
+        else:
+            # d gated on the plain epilogue, then the SwiGLU derivative as one HBM-bound pass over h13 / dh13: the pass is
+            # bound by the 8.6 GB it moves either way, and the streaming kernel keeps more bytes in flight than a GEMM
+            # epilogue can (measured: 1.2 + 1.5 ms against 4.4 ms fused at M = 524288)
+            dg = gemm_nt(g2, w2b.t().contiguous(), None, EPI_STORE, name="gemm_dgated")
+            dh13 = torch.empty_like(h13)
+            M, H = dg.shape
+            with timed("swiglu_bwd", 0.0):
+                check(lib().fk_swiglu_backward_blocked(ptr(h13), ptr(dg), ptr(dh13), M, H, 128, stream()),
+                      "fk_swiglu_backward_blocked")
+            del dg
         dw2 = gemm_tn(g2, gated, name="gemm_w2_dw").to(ctx.w_dtype)
         dx = gemm_nt(dh13, w13.t().contiguous(), None, EPI_STORE, name="gemm_w13_dx").view(ctx.in_shape)
         if dx.dtype != ctx.in_dtype and ctx.in_dtype in (torch.float32, torch.float16):

@@ -122,6 +122,9 @@ int fk_norm_backward(const void* x, int x_dtype, const void* g, int g_dtype, con
 /* MLP gate silu(w1 x) * (w3 x) (brainformer.py:123-124) on the fused bf16 projection h13 [M, 2H]. */
 int fk_swiglu_forward(const void* h13, void* y, long long M, int H, void* stream);
 int fk_swiglu_backward(const void* h13, const void* gy, void* dh13, long long M, int H, void* stream);
+/* the same derivative on the block-interleaved h13 / dh13 of fk_gemm_nt's SwiGLU epilogue ([w1 block | w3 block] per
+ * `block` hidden units); gy [M, H] in hidden-unit order. */
+int fk_swiglu_backward_blocked(const void* h13, const void* gy, void* dh13, long long M, int H, int block, void* stream);
 /* apply_rope (brainformer.py:70-91) in place on bf16 [B,S,H,32] (strides in elements); table [P,16,2] fp32
  * (cos,sin) = view_as_real(build_complex_rope_cache); pos (nullable) [B,S] int32 else position = s + pos_offset. */
 int fk_rope(void* x, long long bs, long long ts, int B, int S, int H, int head_dim, const float* table, int P,
@@ -223,6 +226,36 @@ int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb, void*
 int fk_gemm_tn_splits(long long M, int Na, int Nb, int max_ctas);
 int fk_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* out, long long M, int Na, int Nb,
                float* ws, int splits, void* stream);
+
+/* ---- input pipeline on the device (utils/data_utils.py) ------------------------------------------------
+ * Ragged trials stored back to back: volt [sum_T, C1] fp32 (spike power), spk [sum_T, C2] fp32 (threshold crossings; C2 = 0
+ * and spk = null for already concatenated data), offsets [n_trials + 1] int64 first row of each trial, block_id [n_trials]
+ * int32 dense recording-block ids in [0, n_blocks).  C1 % 4 == 0, C2 % 4 == 0.
+ *
+ * fk_input_trial_moments: part [n_trials, C1 + C2] fp64 = per trial and channel sum of x (mean == null) or of
+ *   (x - mean[block])^2 (mean = fp64 [n_blocks, C] from pass 0).
+ * fk_input_block_reduce: adds the trials' partial sums per block in trial order.  pass 0 -> mean_d (fp64) and mean_f
+ *   (fp32); pass 1 -> std_f (population std, as np.std / StandardScaler) with zero_policy 0: std == 0 -> 1
+ *   (process_signal, data_utils.py:142) or 1: std < 10 eps -> 1 (StandardScaler, z_score_per_block_scaling :78-109).
+ * fk_input_normalize: out [n_trials, T_out, C1 + C2] (out_dtype 0 = f32, 1 = bf16) = (x - mean) / std per block, smoothed
+ *   over the trial's own bins with scipy's gaussian_filter1d(sigma = 1) when smooth != 0 (process_signal :115-156),
+ *   zero padded / truncated to T_out bins (pad_truncate_brain_list :243-267). */
+int fk_input_trial_moments(const float* volt, const float* spk, const long long* offsets, const int* block_id,
+                           int n_trials, int C1, int C2, const double* mean, double* part, void* stream);
+int fk_input_block_reduce(const double* part, const long long* offsets, const int* block_id, int n_trials, int n_blocks,
+                          int C, int pass, int zero_policy, double* mean_d, float* mean_f, float* std_f, void* stream);
+int fk_input_normalize(const float* volt, const float* spk, const long long* offsets, const int* block_id, const float* mean,
+                       const float* stdv, int n_trials, int C1, int C2, int T_out, int smooth, void* out, int out_dtype,
+                       void* stream);
+
+/* ---- encoder -> GPT-2 prefix hand-off (models/gpt2_model.py:178-196) -------------------------------------
+ * out [B, Tc + T, D] = cat([prefix [B, Tc, D], wte[idx [B, T]]], dim 1) + wpe[0 .. Tc + T); wte [V, D], wpe [P, D] fp32;
+ * prefix / out dtype 0 = f32, 1 = bf16; idx int64.  Backward: g [B, Tc + T, D] fp32 -> dwte [V, D] += scatter of the token
+ * rows (fp32 atomics), dwpe [P, D] rows [0, Tc + T) += sum over the batch; d prefix is the view g[:, :Tc]. */
+int fk_prefix_embed_forward(const void* prefix, int prefix_dtype, const long long* idx, const float* wte, const float* wpe,
+                            void* out, int out_dtype, int B, int Tc, int T, int D, int V, int P, void* stream);
+int fk_prefix_embed_backward(const float* g, const long long* idx, float* dwte, float* dwpe, int B, int Tc, int T, int D,
+                             int V, void* stream);
 
 #ifdef __cplusplus
 }

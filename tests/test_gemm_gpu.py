@@ -110,9 +110,12 @@ def test_gemm_tn_matches_fp32_matmul(M, Na, Nb):
     assert torch.equal(out, gemm.gemm_tn(a, b)), "the split reduction must be bit-reproducible"
 
 
-def test_linear_qkv_mlp_functions_match_torch():
-    """The autograd Functions (forward + all gradients) against fp32 PyTorch on the same weights."""
+@pytest.mark.parametrize("mlp_bwd", ["split", "fused"])
+def test_linear_qkv_mlp_functions_match_torch(mlp_bwd, monkeypatch):
+    """The autograd Functions (forward + all gradients) against fp32 PyTorch on the same weights; the MLP backward both as
+    d-gated GEMM + streaming SwiGLU derivative (default) and with the derivative in the GEMM epilogue."""
     from frankenstein_b200 import gemm
+    monkeypatch.setattr(gemm, "MLP_BWD", mlp_bwd)
     from frankenstein_b200.brainformer import apply_rope, build_complex_rope_cache
     from frankenstein_b200.ops import RopeSpec
     g = torch.Generator().manual_seed(0)
