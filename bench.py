@@ -162,7 +162,10 @@ class ClockSampler:
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            # (every query takes the driver's lock: at 100 ms the poll itself cost the step ~2 %; 500 ms still gives several
+            #  samples under load per timed region)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          os.environ.get("FK_CLOCK_POLL_MS", "500"),
                                           "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -575,6 +578,10 @@ def main():
     clocks.start()
     _lib.reset_launch_count()
     _lib.TIMER.reset()
+    # inside the timed region only the attention and codeword-search launches carry event pairs (13 per step: the
+    # dominant kernel and the headline kernel); every other kernel is timed in a separate instrumented pass below, so
+    # that ~2 x 240 event records per step do not sit in the number that is reported
+    _lib.TIMER.only = ("attn_", "vq_search")
     _lib.TIMER.enabled = True
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -602,6 +609,16 @@ def main():
     ksum = _lib.TIMER.summary()
     clk = clocks.stop()
     final_loss = float(loss.detach())
+    # ---- instrumented pass (not part of `value`): event pairs around every kernel of the library ----
+    K2 = min(K, 3)
+    _lib.TIMER.reset()
+    _lib.TIMER.only = None
+    _lib.TIMER.enabled = True
+    for i in range(K2):
+        step(*pool[i % n_pool])
+    _lib.TIMER.enabled = False
+    ksum_all = _lib.TIMER.summary()
+    barrier()
 
     # ---- timed region 2: end to end.  Every step copies its pinned host batch to the device (on a copy stream, one
     #      batch ahead of the compute, double buffered) and reads the loss back (utils/train_utils.py:147) ----
@@ -652,18 +669,20 @@ def main():
         if wl in ("cfg4-joint", "cfg2-encoder"):
             traffic.update({k: int(v * B / 16) for k, v in NCU_TRAFFIC_PER_16_TRIALS.items()})
         kern = {}
-        for name, (n, ms, work) in ksum.items():
-            if work <= 0 or ms <= 0:
-                continue
-            avg_ms = ms / n
-            ach = work / (ms * 1e-3) / 1e12
-            kern[name] = {"kernel": KERNEL_NAMES.get(name, name), "bound": "tensor", "achieved": ach, "peak": tc_peak,
-                          "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": traffic.get(name),
-                          "algorithmic_flops_per_launch": work / n, "avg_launch_ms": avg_ms, "launches_timed": n,
-                          "ms_per_step": ms / K, "peak_source": peak_src}
+        for src, steps_timed, where in ((ksum_all, K2, "separate instrumented pass"), (ksum, K, "timed region")):
+            for name, (n, ms, work) in src.items():
+                if work <= 0 or ms <= 0:
+                    continue
+                avg_ms = ms / n
+                ach = work / (ms * 1e-3) / 1e12
+                kern[name] = {"kernel": KERNEL_NAMES.get(name, name), "bound": "tensor", "achieved": ach, "peak": tc_peak,
+                              "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": traffic.get(name),
+                              "algorithmic_flops_per_launch": work / n, "avg_launch_ms": avg_ms, "launches_timed": n,
+                              "ms_per_step": ms / steps_timed, "peak_source": peak_src, "measured_in": where}
         roof = None
         if kern:
-            dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+            dom = max((k for k in kern if kern[k]["measured_in"] == "timed region"), key=lambda k: kern[k]["ms_per_step"],
+                      default=max(kern, key=lambda k: kern[k]["ms_per_step"]))
             roof = dict(kern[dom])
             roof["share_of_step"] = roof["ms_per_step"] / (ms_total / K)
         groups = {}

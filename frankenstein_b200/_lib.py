@@ -169,6 +169,7 @@ class KernelTimer:
 
     def __init__(self):
         self.enabled = False
+        self.only = None          # tuple of name prefixes to record (None = every timed call)
         self.records = []
 
     def reset(self):
@@ -191,13 +192,14 @@ class timed:
         self.name, self.work = name, work
 
     def __enter__(self):
-        if TIMER.enabled:
+        self.on = TIMER.enabled and (TIMER.only is None or self.name.startswith(TIMER.only))
+        if self.on:
             self.a = torch.cuda.Event(enable_timing=True)
             self.a.record()
         return self
 
     def __exit__(self, *exc):
-        if TIMER.enabled:
+        if self.on:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
             TIMER.records.append((self.name, self.a, b, self.work))

@@ -171,8 +171,15 @@ class CausalSelfAttention(nn.Module):
             return _linear_bf16(res, self.project.weight)
         wqkv = torch.cat([self.qw.weight, self.kw.weight, self.vw.weight], dim=0)
         qkv = _linear_bf16(x, wqkv)
+        small_ok = (attn_mask is None and self.head_dim != 32 and ops.small_attention_supported(T, self.head_dim)
+                    and (rope is None or (isinstance(rope, torch.Tensor) and rope.dim() == 2)))
         if kernel_ok:
             res = ops.attention_qkv(qkv, self.n_heads, spec, attn_mask)
+        elif small_ok:
+            # the perceiver's self-attention Block (<= 64 tokens, head_dim 16): RoPE applied on load inside the kernel
+            rs = None if rope is None else RopeSpec.from_complex(rope, T, last=True)       # reference convention: rope[-T:]
+            q, k, v = qkv.view(B, T, 3, inner).unbind(2)
+            res = ops.small_attention(q, k, v, self.n_heads, rope=rs)
         else:
             q, k, v = qkv.view(B, T, 3, self.n_heads, self.head_dim).unbind(2)
             if isinstance(rope, RopeSpec):
@@ -205,14 +212,20 @@ class CausalCrossAttention(nn.Module):
     def forward(self, x, context, attn_mask=None, use_kv_cache=None):
         B, T, _ = x.shape
         S = context.shape[1]
-        q = _linear_bf16(x, self.qw.weight).view(B, T, self.n_heads, -1).transpose(1, 2)
+        q = _linear_bf16(x, self.qw.weight)
         # two projections instead of one fused [k|v] GEMM: slicing a fused buffer costs a zero-fill + strided copy per
         # slice in autograd (select_backward), more than the second GEMM launch
         ctx_bf16 = context.to(BF16)
-        k = _linear_bf16(ctx_bf16, self.kw.weight).view(B, S, self.n_heads, -1).transpose(1, 2)
-        v = _linear_bf16(ctx_bf16, self.vw.weight).view(B, S, self.n_heads, -1).transpose(1, 2)
-        res = _dense_mask_attention(q, k, v, attn_mask)
-        res = res.transpose(1, 2).reshape(B, T, -1)
+        k = _linear_bf16(ctx_bf16, self.kw.weight)
+        v = _linear_bf16(ctx_bf16, self.vw.weight)
+        hd = q.shape[-1] // self.n_heads
+        if attn_mask is None and x.is_cuda and ops.small_attention_supported(T, hd):
+            # few learnable queries against thousands of context tokens: the split-key kernel of csrc/small_attention.cu
+            res = ops.small_attention(q, k, v, self.n_heads)
+        else:
+            q, k, v = (t.view(B, t.shape[1], self.n_heads, -1).transpose(1, 2) for t in (q, k, v))
+            res = _dense_mask_attention(q, k, v, attn_mask)
+            res = res.transpose(1, 2).reshape(B, T, -1)
         return _linear_bf16(res, self.project.weight)
 
 
@@ -370,8 +383,19 @@ class Encoder(nn.Module):
 
     def forward(self, x, kv_cache=None, out_dtype=torch.float32):
         """out_dtype: dtype of the final LayerNorm output (the perceiver asks for bf16, the operand type of its GEMMs)."""
-        patches = self.to_patches(x)
-        b, n_tokens, _ = patches.shape
+        b, T, E = x.shape
+        if T % self.patch_size != 0:
+            raise ValueError(f"window of {T} bins is not divisible by patch_size {self.patch_size}")
+        n_tokens = (T // self.patch_size) * E
+        w_emb = self.transformer.emb
+        fused = (GEMM_IMPL == "own" and x.is_cuda and not x.requires_grad
+                 and gemm.patch_embed_supported(T, E, self.patch_size, w_emb.weight.shape[0]))
+        if fused:
+            # patchify + Linear(p -> dim) + bias as ONE tcgen05 contraction fed by TMA straight from x (csrc/gemm.cu,
+            # fk_patch_embed_forward): the [B, S, p] patch tensor of `to_patches` is never written
+            h_delta = gemm.patch_embed(x, w_emb.weight, w_emb.bias)
+        else:
+            h_delta = self.embed(self.to_patches(x))
         emb = self.spatial_pos_embedding[:, -n_tokens:].float()       # [1, S, dim]; added inside the first add+LayerNorm
         mask = LabelMask.block_causal(b, n_tokens, self.n_electrodes, x.device)
         if n_tokens != self.block_size:
@@ -380,7 +404,7 @@ class Encoder(nn.Module):
             ids = ((torch.arange(n_tokens, device=x.device) + first) // self.n_electrodes).to(torch.int32)
             mask = LabelMask(ids[None].expand(b, n_tokens).contiguous())
         rope = RopeSpec(self.rope_table(), None, self.block_size - n_tokens)
-        _, y = run_blocks(self.transformer.h, emb, mask, rope, self.transformer.ln_f, out_dtype, h_delta=self.embed(patches))
+        _, y = run_blocks(self.transformer.h, emb, mask, rope, self.transformer.ln_f, out_dtype, h_delta=h_delta)
         return y
 
 

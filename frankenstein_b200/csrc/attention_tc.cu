@@ -587,6 +587,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         tmem_st8(taddr + 64 + i * 8, dw);
 #endif
       }
+#if FK_ATTN_EXP == 8
+      // cost probe for a single-pass backward: the dQ partial of this tile ([64 queries x 32] fp32) reduced into global
+      // memory with vector reds, 4 per thread (targets: the dV / dK output rows of the tile's queries -- results are WRONG)
+      if (MODE == MODE_DKV) {
+        const int qrow = (tile_list[j] & 0x7fff) * kCols + (tid & 63);
+        if (qrow < p.S_col) {
+          __nv_bfloat16* base16 = ((tid >> 6) ? p.out1 + b * p.o1_bs + static_cast<long long>(qrow) * p.o1_ts
+                                              : p.out0 + b * p.o0_bs + static_cast<long long>(qrow) * p.o0_ts) + h * 32;
+          float* dst = reinterpret_cast<float*>(base16);
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + v4 * 4), "f"(0.f), "f"(0.f), "f"(0.f), "f"(0.f) : "memory");
+        }
+      }
+#endif
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -980,18 +995,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t o_addr = tmem_base + lane_base + 384 + g * 32;
     float m_run = -INFINITY, l_run = 0.f, alpha_pend = 1.f;
     int pre_i = 0;
+    // key labels of a tile are only fetched and staged for tiles that need the per-element compare (warp-group uniform
+    // flag from the tile list): fully visible tiles -- every tile of the block-causal mask when the electrode count is a
+    // multiple of the tile sizes -- cost neither the global load nor the warpgroup barrier
+    const uint16_t my_flag = (g == 0) ? 0x4000 : 0x8000;
     auto prefetch = [&](int j) {
-      if (j >= T) return;
+      if (j >= T || !(tile_list[j] & my_flag)) return;
       const int c = (tile_list[j] & 0x3fff) * kFwdTileK + tid;
       pre_i = (c < p.Sk) ? (masked ? p.kid[static_cast<long long>(b) * p.Sk + c] : 0) : 0x7fffffff;
     };
     prefetch(0);
     for (int j = 0; j < T; ++j) {
       const int gj = base + j;                       // key-tile counter across items (barrier parities)
-      const bool need_mask = (tile_list[j] & (g == 0 ? 0x4000 : 0x8000)) != 0;
-      int* s_id = ids_base + (gj & 1) * 128;
-      s_id[tid] = pre_i;
-      named_bar_sync(1 + g, 128);
+      const bool need_mask = (tile_list[j] & my_flag) != 0;
+      int* s_id = ids_base;
+      if (need_mask) {
+        named_bar_sync(1 + g, 128);                  // the previous masked tile's readers are done with the buffer
+        s_id[tid] = pre_i;
+        named_bar_sync(1 + g, 128);
+      }
       prefetch(j + 1);
       mbar_wait(&s_full[g], gj & 1);
       tc_fence_after();

@@ -391,7 +391,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     int stage = 0;
-    uint32_t phase = 0, it = 0, nload = 0;
+    uint32_t phase = 0, it = 0;
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
       for (int t = 0; t < p.ntile; ++t) {
         for (int j = 0; j < nkb; ++j) {
@@ -405,8 +405,6 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
             __syncwarp();
           }
-          if ((p.dbg & 32) && nload >= static_cast<uint32_t>(p.nstage)) continue;     // diagnosis: B ring filled once, never reloaded
-          ++nload;
           mbar_wait(&b_empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&b_full[stage], kBStageBytes);
@@ -423,51 +421,37 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t as_addr = smem_u32(As), bs_addr = smem_u32(Bs);
     int stage = 0;
-    uint32_t phase = 0, it = 0, tc = 0, nuse = 0;
-    long long w_te = 0, w_a = 0, w_b = 0;                   // diagnosis (FK_GEMM_DBG & 16): cycles blocked per barrier kind
-    const bool prof = (p.dbg & 16) != 0;
-    const long long t_begin = prof ? clock64() : 0;
-    auto timed_wait = [&](uint64_t* bar, uint32_t ph, long long& acc) {
-      if (prof) {
-        if (mbar_test_wait(bar, ph)) return;
-        const long long t0 = clock64();
-        mbar_wait(bar, ph);
-        acc += clock64() - t0;
-      } else {
-        mbar_wait(bar, ph);
-      }
-    };
+    uint32_t phase = 0, it = 0, tc = 0;
+    // (the loop body is kept minimal: one issuing warp has to turn a 16 KB stage around in the 256 cycles its two MMAs
+    //  take -- every integer division, diagnostic branch or descriptor rebuild in here showed up in the GEMM's time)
+    const uint64_t adesc0 = umma_desc_sw128(as_addr), bdesc0 = umma_desc_sw64(bs_addr);
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
       for (int t = 0; t < p.ntile; ++t, ++tc) {
         const uint32_t as = tc & 1;
-        timed_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1, w_te);
+        mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + as * 256;
+        const bool first_tile = t == 0, last_tile = t == p.ntile - 1;
+        uint64_t adesc = adesc0;      // 64-byte half (j & 1) of slab j / 2: +4 within a slab, + slab size - 4 to the next
         for (int j = 0; j < nkb; ++j) {
-          const int ks = j >> 1;
-          if (t == 0 && (j & 1) == 0) timed_wait(&a_full[ks], it & 1, w_a);
-          if (!(p.dbg & 32) || nuse < static_cast<uint32_t>(p.nstage)) timed_wait(&b_full[stage], phase, w_b);
-          ++nuse;
+          if (first_tile && (j & 1) == 0) mbar_wait(&a_full[j >> 1], it & 1);
+          mbar_wait(&b_full[stage], phase);
           tc_fence_after();
-          // A: 64-byte half (j & 1) of the 128-byte swizzled rows of slab ks; a K step of 16 elements = +32 B = +2
-          const uint64_t adesc = umma_desc_sw128(as_addr + ks * kASlabBytes) + 4 * (j & 1);
-          const uint64_t bdesc = umma_desc_sw64(bs_addr + stage * kBStageBytes);
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (kBStageBytes >> 4));
           if (elect_one()) {
             umma_bf16(d_tmem, adesc, bdesc, idesc, j != 0);
             umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
             umma_commit(&b_empty[stage]);
-            if (t == p.ntile - 1 && ((j & 1) == 1 || j == nkb - 1)) umma_commit(&a_empty[ks]);
+            if (last_tile && ((j & 1) == 1 || j == nkb - 1)) umma_commit(&a_empty[j >> 1]);
           }
           __syncwarp();
+          adesc += (j & 1) ? static_cast<uint64_t>((kASlabBytes >> 4) - 4) : 4ull;
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         }
         if (elect_one()) umma_commit(&tmem_full[as]);
         __syncwarp();
       }
     }
-    if (prof && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-      printf("gemm_res<%d> cta %d: issuer total %lld cycles, %u tiles; blocked on tmem_empty %lld, a_full %lld, b_full %lld\n", EPI,
-             static_cast<int>(blockIdx.x), clock64() - t_begin, tc, w_te, w_a, w_b);
   } else if (warp >= 4) {
     // ================================ epilogue ================================
     const int e = warp - 4;
@@ -631,7 +615,13 @@ struct TnParams {
   float* ws;                 // [splits][Na][Nb]
   long long M;
   int Na, Nb, ta, tb, splits, nstage;
-  long long rows_per_split;  // multiple of 64
+  long long rows_per_split;  // multiple of krows
+  int krows;                 // rows of the contraction per pipeline stage (64; the patch size for the patch embedding)
+  // patch-embedding mode (fk_patch_embed_forward): every row range is one (trial, time patch) and its [Na, Nb] product IS
+  // the projection of that patch's Na tokens -- written as bf16 rows with the bias (and the electrode embedding) added
+  __nv_bfloat16* out_bf16;   // [splits * Na, Nb] or null
+  const float* bias;         // [Nb] or null
+  const float* emb;          // [Na, Nb] or null
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -677,13 +667,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int ia = tile / p.tb, ib = tile % p.tb;
       long long k0, k1;
       k_range(split, k0, k1);
-      for (long long k = k0; k < k1; k += 64) {
+      for (long long k = k0; k < k1; k += p.krows) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* st = smem + stage * kStage;
-          mbar_expect_tx(&full[stage], kStage);
-          tma_load_3d(st, &tm_a, &full[stage], 0, static_cast<int>(k), ia * 4);              // box 64 x 64 rows x 4 chunks
-          tma_load_3d(st + kBSlabBytes, &tm_b, &full[stage], 0, static_cast<int>(k), ib * 4);
+          mbar_expect_tx(&full[stage], static_cast<uint32_t>(2 * 4 * p.krows * 128));
+          tma_load_3d(st, &tm_a, &full[stage], 0, static_cast<int>(k), ia * 4);              // box 64 x krows rows x 4 chunks
+          // (patch-embedding mode: B = W^T [patch, dim] is the same for every row range -> row coordinate within the range)
+          tma_load_3d(st + kBSlabBytes, &tm_b, &full[stage], 0, static_cast<int>(p.out_bf16 ? k - k0 : k), ib * 4);
         }
         __syncwarp();
         if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -702,18 +693,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_wait(tmem_empty, (uc & 1) ^ 1);
       tc_fence_after();
       bool first = true;
-      for (long long k = k0; k < k1; k += 64) {
+      const uint32_t chunk_bytes = static_cast<uint32_t>(p.krows) * 128u;      // one 64-column chunk of a stage
+      const int nkk = p.krows >> 4;
+      for (long long k = k0; k < k1; k += p.krows) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t st = s_addr + stage * kStage;
-        const uint64_t a0 = umma_desc_mn_sw128(st, 8192), a1 = umma_desc_mn_sw128(st + 2 * 8192, 8192);
-        const uint64_t bdesc = umma_desc_mn_sw128(st + kBSlabBytes, 8192);
+        const uint64_t a0 = umma_desc_mn_sw128(st, chunk_bytes), a1 = umma_desc_mn_sw128(st + 2 * chunk_bytes, chunk_bytes);
+        const uint64_t bdesc = umma_desc_mn_sw128(st + kBSlabBytes, chunk_bytes);
         if (elect_one()) {
           // a K step of 16 rows = 2048 B = +128 in the (address >> 4) field
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_u, a0 + 128 * kk, bdesc + 128 * kk, idesc, !(first && kk == 0));
+          for (int kk = 0; kk < 4; ++kk)
+            if (kk < nkk) umma_bf16(tmem_u, a0 + 128 * kk, bdesc + 128 * kk, idesc, !(first && kk == 0));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_u + 256, a1 + 128 * kk, bdesc + 128 * kk, idesc, !(first && kk == 0));
+          for (int kk = 0; kk < 4; ++kk)
+            if (kk < nkk) umma_bf16(tmem_u + 256, a1 + 128 * kk, bdesc + 128 * kk, idesc, !(first && kk == 0));
           umma_commit(&empty[stage]);
         }
         __syncwarp();
@@ -752,10 +747,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (lane == 0) mbar_arrive(tmem_empty);
         }
         if (row_ok && ib * 256 + c * 32 < p.Nb) {
+          if (p.out_bf16 != nullptr) {
+            const int col = ib * 256 + c * 32;
+            float v[32];
+            to_f32(r[c & 1], v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<uint4*>(dst + c * 32 + i * 4) =
-                make_uint4(r[c & 1][i * 4], r[c & 1][i * 4 + 1], r[c & 1][i * 4 + 2], r[c & 1][i * 4 + 3]);
+            for (int i = 0; i < 8; ++i) {
+              float4 add = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.emb != nullptr) {
+                const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.emb + static_cast<long long>(row) * p.Nb + col) + i);
+                add.x += e4.x; add.y += e4.y; add.z += e4.z; add.w += e4.w;
+              }
+              v[4 * i] += add.x; v[4 * i + 1] += add.y; v[4 * i + 2] += add.z; v[4 * i + 3] += add.w;
+            }
+            store32_bf16(p.out_bf16 + (static_cast<long long>(split) * p.Na + row) * p.Nb + col, v);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<uint4*>(dst + c * 32 + i * 4) =
+                  make_uint4(r[c & 1][i * 4], r[c & 1][i * 4 + 1], r[c & 1][i * 4 + 2], r[c & 1][i * 4 + 3]);
+          }
         }
       }
     }
@@ -930,12 +941,13 @@ FK_API int fk_gemm_tn(const void* A, long long lda, const void* B, long long ldb
   const int G = fk_sm_count();
   FK_REQUIRE(G > 0 && splits == fk_gemm_tn_splits(M, Na, Nb, G), "fk_gemm_tn: split count does not match fk_gemm_tn_splits");
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_chunks(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(Na), static_cast<uint64_t>(lda));
-  rc |= make_tmap_bf16_chunks(&tb, B, static_cast<uint64_t>(M), static_cast<uint64_t>(Nb), static_cast<uint64_t>(ldb));
+  int rc = make_tmap_bf16_chunks(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(Na), static_cast<uint64_t>(lda), 64);
+  rc |= make_tmap_bf16_chunks(&tb, B, static_cast<uint64_t>(M), static_cast<uint64_t>(Nb), static_cast<uint64_t>(ldb), 64);
   if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
   TnParams p = {};
   p.ws = ws; p.M = M; p.Na = Na; p.Nb = Nb; p.ta = (Na + 255) / 256; p.tb = (Nb + 255) / 256; p.splits = splits;
   p.rows_per_split = ((M + splits - 1) / splits + 63) / 64 * 64;
+  p.krows = 64;
   p.nstage = 3;
   const int smem_bytes = p.nstage * 2 * kBSlabBytes + 512;
   const long long n_units = static_cast<long long>(p.ta) * p.tb * splits;
@@ -949,5 +961,47 @@ FK_API int fk_gemm_tn(const void* A, long long lda, const void* B, long long ldb
   gemm_tn_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(ws, out, n4, splits);
   FK_CHECK_LAUNCH();
   fk_count_launch(2);
+  return FK_OK;
+}
+
+// Patch embedding of brainformer.Encoder (models/brainformer.py:282 `to_patches` 'b (t p1) c -> b (t c) p1', :285 / :338-343
+// Linear(p1 -> dim) with bias, + the electrode embedding): token (trial b, patch t, electrode c) = x[b, t p1 .. t p1 + p1, c].
+// With x viewed as the row-major matrix [B T, E], the p1 rows of one (b, t) ARE the transposed patch matrix of that
+// patch's E tokens, so the projection of those tokens is the TN product  x_bt[p1, E]^T  Wt[p1, dim]: the gemm_tn kernel
+// with one row range per patch, both operands read MN-major by TMA straight from x and W^T -- the patch tensor
+// [B, S, p1] of the reference (a transposed copy) never exists.  Epilogue: + bias (+ emb [E, dim]) -> bf16 [B S, dim].
+FK_API int fk_patch_embed_forward(const void* x_bf16, long long ldx, const void* wt_bf16, const float* bias, const float* emb,
+                                  void* out_bf16, long long n_rows, int E, int patch, int dim, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(x_bf16 && wt_bf16 && out_bf16 && n_rows > 0 && E > 0 && patch > 0 && dim > 0, "fk_patch_embed_forward: bad argument");
+  FK_REQUIRE(patch % 16 == 0 && patch <= 64 && n_rows % patch == 0, "fk_patch_embed_forward: patch size must be 16, 32, 48 or 64 and divide the rows");
+  FK_REQUIRE(E % 64 == 0 && dim % 64 == 0 && ldx % 8 == 0 && ldx >= E, "fk_patch_embed_forward: electrodes and dim must be multiples of 64");
+  FK_REQUIRE(n_rows < (1ll << 31) - 64, "fk_patch_embed_forward: too many rows");
+  FK_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(wt_bf16) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, "fk_patch_embed_forward: pointers must be 16-byte aligned");
+  const int G = fk_sm_count();
+  FK_REQUIRE(G > 0, "fk_patch_embed_forward: no device");
+  CUtensorMap ta, tb;
+  // A = x: rows = (trial, bin), Na = electrodes.  B = W^T [patch, dim]: the same rows for every row range (the producer
+  // gives B the row coordinate within the range).
+  int rc = make_tmap_bf16_chunks(&ta, x_bf16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(E), static_cast<uint64_t>(ldx),
+                                 static_cast<uint32_t>(patch));
+  rc |= make_tmap_bf16_chunks(&tb, wt_bf16, static_cast<uint64_t>(patch), static_cast<uint64_t>(dim), static_cast<uint64_t>(dim),
+                              static_cast<uint32_t>(patch));
+  if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
+  TnParams p = {};
+  p.ws = nullptr; p.M = n_rows; p.Na = E; p.Nb = dim; p.ta = (E + 255) / 256; p.tb = (dim + 255) / 256;
+  p.splits = static_cast<int>(n_rows / patch);
+  p.rows_per_split = patch; p.krows = patch; p.nstage = 3;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); p.bias = bias; p.emb = emb;
+  const int smem_bytes = p.nstage * 2 * kBSlabBytes + 512;
+  const long long n_units = static_cast<long long>(p.ta) * p.tb * p.splits;
+  const unsigned grid = static_cast<unsigned>(n_units < G ? n_units : G);
+  static bool done[FK_MAX_DEVICES];
+  const int r2 = set_smem_attr(gemm_tn_kernel, done[fk_device_ordinal()], kGemmSmemLimit);
+  if (r2 != FK_OK) return r2;
+  gemm_tn_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, p);
+  FK_CHECK_LAUNCH();
+  fk_count_launch(1);
   return FK_OK;
 }

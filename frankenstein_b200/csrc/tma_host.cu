@@ -55,10 +55,10 @@ int make_tmap_bf16_2d_sw64(CUtensorMap* map, const void* base, uint64_t rows, ui
   return make_tmap_bf16(map, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
-int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   const uint64_t dims[3] = {64, rows, cols / 64};
   const uint64_t strides[2] = {ld * 2, 128};
-  const uint32_t box[3] = {64, 64, 4};
+  const uint32_t box[3] = {64, box_rows, 4};
   return make_tmap_bf16(map, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 

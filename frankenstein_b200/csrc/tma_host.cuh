@@ -22,7 +22,7 @@ int make_tmap_bf16_2d_sw64(CUtensorMap* map, const void* base, uint64_t rows, ui
 
 // The same matrix as an MN-major operand source: dims (64 columns of a chunk, rows, chunk index), box = 64 x 64 rows x 4
 // chunks -> shared memory [chunk][row][64 elements] (8 KB per chunk), 128-byte swizzle.  cols % 64 == 0.
-int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);
+int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 // bf16 [B][S][H][32] with token / batch strides (elements): box = one head's 32 columns x box_rows tokens,
 // 64-byte swizzle.  Coordinates: (0, head, token, batch).

@@ -231,10 +231,16 @@ vq_ema_count_kernel(const long long* __restrict__ indices, long long N, int K, i
   if (k >= 0 && k < K) atomicAdd(count + k, 1);          // integer: order independent
 }
 
-// single block: offs[k] = exclusive prefix of count; cursor[k] = 0
+constexpr int kSegShort = 32;      // segments up to this many rows are summed by one warp (rank sort in registers)
+constexpr int kSegSort = 1024;     // up to this many: one CTA sorts the row ids in shared memory; beyond: row scan
+
+// single block: offs[k] = exclusive prefix of count; cursor[k] = 0; long_list = codes with more than kSegShort rows
 __global__ void __launch_bounds__(1024)
-vq_ema_scan_kernel(const int* __restrict__ count, int K, int* __restrict__ offs, int* __restrict__ cursor) {
+vq_ema_scan_kernel(const int* __restrict__ count, int K, int* __restrict__ offs, int* __restrict__ cursor,
+                   int* __restrict__ n_long, int* __restrict__ long_list) {
   __shared__ int scan[1024];
+  __shared__ int s_long;
+  if (threadIdx.x == 0) s_long = 0;
   const int per = (K + blockDim.x - 1) / blockDim.x;
   const int k0 = min(K, static_cast<int>(threadIdx.x) * per), k1 = min(K, k0 + per);
   int sum = 0;
@@ -251,8 +257,12 @@ vq_ema_scan_kernel(const int* __restrict__ count, int K, int* __restrict__ offs,
   for (int k = k0; k < k1; ++k) {
     offs[k] = run;
     cursor[k] = 0;
-    run += count[k];
+    const int c = count[k];
+    run += c;
+    if (c > kSegShort) long_list[atomicAdd(&s_long, 1)] = k;      // (any order: every long code is summed on its own)
   }
+  __syncthreads();
+  if (threadIdx.x == 0) *n_long = s_long;
 }
 
 __global__ void __launch_bounds__(256)
@@ -285,7 +295,8 @@ vq_ema_segsum_kernel(const float* __restrict__ xn, const int* __restrict__ count
       }
     }
   };
-  if (c <= 32) {
+  if (c > kSegShort) return;         // a hot code: vq_ema_segsum_long_kernel
+  {
     // rank sort inside the warp: lane i holds one row id; the lane whose rank is t supplies the t-th row
     const int id = lane < c ? seg[lane] : 0x7fffffff;
     int rank = 0;
@@ -295,20 +306,6 @@ vq_ema_segsum_kernel(const float* __restrict__ xn, const int* __restrict__ count
       const unsigned m = __ballot_sync(0xffffffffu, rank == t && lane < c);
       add_row(__shfl_sync(0xffffffffu, id, __ffs(m) - 1));
     }
-  } else {
-    // long segment (a hot code): repeatedly take the smallest row id above the last one added
-    int last = -1;
-    for (int t = 0; t < c; ++t) {
-      int best = 0x7fffffff;
-      for (int j = lane; j < c; j += 32) {
-        const int v = seg[j];
-        best = (v > last && v < best) ? v : best;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-      add_row(best);
-      last = best;
-    }
   }
   float* dst = stats + static_cast<long long>(k) * D;
 #pragma unroll
@@ -317,6 +314,78 @@ vq_ema_segsum_kernel(const float* __restrict__ xn, const int* __restrict__ count
     if (d < D) *reinterpret_cast<float4*>(dst + d) = acc[i];
   }
   if (lane == 0) stats[static_cast<long long>(K) * D + k] = static_cast<float>(c);
+}
+
+// Hot codes (more than kSegShort rows): one CTA of 32 warps per code.  The rows are brought into ascending order -- up
+// to kSegSort ids by a bitonic sort in shared memory, beyond that by scanning the index array itself, which is in row
+// order -- cut into 32 contiguous ranges, each summed by one warp in order, and the 32 partial sums are added in warp
+// order: a fixed summation tree for a given assignment, whatever order the fill kernel's atomics produced.
+__global__ void __launch_bounds__(1024)
+vq_ema_segsum_long_kernel(const float* __restrict__ xn, const long long* __restrict__ indices, long long N,
+                          const int* __restrict__ count, const int* __restrict__ offs, const int* __restrict__ list,
+                          const int* __restrict__ n_long, const int* __restrict__ long_list, int K, int D,
+                          float* __restrict__ stats) {
+  __shared__ int ids[kSegSort];
+  __shared__ float part[32][256];
+  if (static_cast<int>(blockIdx.x) >= *n_long) return;
+  const int k = long_list[blockIdx.x];
+  const int c = count[k];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  auto add_row = [&](long long row) {
+    const float* xr = xn + row * D;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int d = lane * 4 + i * 128;
+      if (d < D) {
+        const float4 x = ldg_nc_f4(xr + d);
+        acc[i].x += x.x; acc[i].y += x.y; acc[i].z += x.z; acc[i].w += x.w;
+      }
+    }
+  };
+  if (c <= kSegSort) {
+    ids[threadIdx.x] = static_cast<int>(threadIdx.x) < c ? list[offs[k] + threadIdx.x] : 0x7fffffff;
+    __syncthreads();
+    for (int size = 2; size <= kSegSort; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const int i = threadIdx.x, j = i ^ stride;
+        if (j > i) {
+          const int a = ids[i], b = ids[j];
+          const bool up = (i & size) == 0;
+          if ((a > b) == up) { ids[i] = b; ids[j] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    const int per = (c + 31) / 32;
+    const int t0 = warp * per, t1 = min(c, t0 + per);
+    for (int t = t0; t < t1; ++t) add_row(ids[t]);
+  } else {
+    // the index array is in row order: warp w takes the w-th 32nd of the rows and adds the ones assigned to this code
+    const long long per = ((N + 31) / 32 + 31) / 32 * 32;
+    const long long r0 = warp * per, r1 = min(N, r0 + per);
+    for (long long r = r0; r < r1; r += 32) {
+      const bool hit = (r + lane < r1) && indices[r + lane] == k;
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      while (m) {
+        add_row(r + (__ffs(m) - 1));
+        m &= m - 1;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int d = lane * 4 + i * 128;
+    if (d < D) *reinterpret_cast<float4*>(&part[warp][d]) = acc[i];
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < D) {
+    float sum = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) sum += part[w][threadIdx.x];
+    stats[static_cast<long long>(k) * D + threadIdx.x] = sum;
+  }
+  if (threadIdx.x == 0) stats[static_cast<long long>(K) * D + k] = static_cast<float>(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -608,7 +677,7 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_finish(const float* 
 extern "C" __attribute__((visibility("default"))) long long fk_vq_finish_partials(long long N) { return (N + kRowsPerBlock - 1) / kRowsPerBlock; }
 
 extern "C" __attribute__((visibility("default"))) long long fk_vq_ema_stats_ws(long long N, int K) {
-  return 3ll * K + N;      // int32 words: count | offs | cursor | row list
+  return 3ll * K + N + N / (kSegShort + 1) + 2;      // int32 words: count | offs | cursor | row list | hot codes | their number
 }
 
 extern "C" __attribute__((visibility("default"))) int fk_vq_ema_stats(const float* xn, const long long* indices, long long N, int K, int D, float* stats,
@@ -622,13 +691,21 @@ extern "C" __attribute__((visibility("default"))) int fk_vq_ema_stats(const floa
   const unsigned nb = static_cast<unsigned>((N + 255) / 256);
   vq_ema_count_kernel<<<nb, 256, 0, stream>>>(indices, N, K, count);
   FK_CHECK_LAUNCH();
-  vq_ema_scan_kernel<<<1, 1024, 0, stream>>>(count, K, offs, cursor);
+  int* long_list = list + N;
+  const long long max_long = N / (kSegShort + 1);
+  int* n_long = long_list + max_long + 1;
+  vq_ema_scan_kernel<<<1, 1024, 0, stream>>>(count, K, offs, cursor, n_long, long_list);
   FK_CHECK_LAUNCH();
   vq_ema_fill_kernel<<<nb, 256, 0, stream>>>(indices, N, K, offs, cursor, list);
   FK_CHECK_LAUNCH();
   vq_ema_segsum_kernel<<<(K + kRowsPerBlock - 1) / kRowsPerBlock, kRowsPerBlock * 32, 0, stream>>>(xn, count, offs, list, K, D, stats);
   FK_CHECK_LAUNCH();
-  fk_count_launch(5);
+  if (max_long > 0) {
+    vq_ema_segsum_long_kernel<<<static_cast<unsigned>(max_long < K ? max_long : K), 1024, 0, stream>>>(xn, indices, N, count, offs, list, n_long,
+                                                                                                  long_list, K, D, stats);
+    FK_CHECK_LAUNCH();
+  }
+  fk_count_launch(6);
   return FK_OK;
 }
 

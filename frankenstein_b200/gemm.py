@@ -264,3 +264,56 @@ def swiglu_mlp(x, w1, w3, w2):
     """w2(silu(w1 x) * (w3 x)) with the gate fused into the w1 | w3 projection (forward) and into the d-gated GEMM
     (backward)."""
     return _SwiGLUMLPFn.apply(x, w1, w3, w2)
+
+
+# ------------------------------------------------------------------------------------------------
+# patch embedding (brainformer.Encoder: to_patches + Linear(patch -> dim) + bias)
+# ------------------------------------------------------------------------------------------------
+def patch_embed_supported(T: int, E: int, patch: int, dim: int) -> bool:
+    return patch in (16, 32, 48, 64) and T % patch == 0 and E % 64 == 0 and dim % 64 == 0
+
+
+class _PatchEmbedFn(torch.autograd.Function):
+    @staticmethod
+    @on_tensor_device
+    def forward(ctx, x, weight, bias):
+        require_cuda(x, weight)
+        require_device()
+        B, T, E = x.shape
+        dim, patch = weight.shape
+        xb = x.detach().to(BF16).contiguous().view(B * T, E)
+        wt = weight.detach().t().contiguous().to(BF16)                      # W^T [patch, dim]
+        bias_f = None if bias is None else bias.detach().float().contiguous()
+        out = torch.empty(B, (T // patch) * E, dim, device=x.device, dtype=BF16)
+        with timed("gemm_patch_embed", 2.0 * B * T * E * dim):
+            check(lib().fk_patch_embed_forward(ptr(xb), E, ptr(wt), ptr(bias_f), None, ptr(out), B * T, E, patch, dim, stream()),
+                  "fk_patch_embed_forward")
+        ctx.save_for_backward(xb)
+        ctx.meta = (B, T, E, patch, dim, weight.dtype, None if bias is None else bias.dtype)
+        return out
+
+    @staticmethod
+    @on_tensor_device
+    def backward(ctx, g):
+        (xb,) = ctx.saved_tensors
+        B, T, E, patch, dim, w_dtype, b_dtype = ctx.meta
+        M = B * (T // patch) * E
+        g2 = _as2d(g)
+        # dW[n, k] = sum over tokens g[token, n] * patch[token, k], db[n] = sum g[token, n]: ONE split-K TN product against
+        # [patches | 1 | 0 ...] (the patch matrix exists only here, 64 bf16 columns per token, never in the forward pass)
+        cols = 64 if patch < 64 else 128
+        ext = torch.zeros(M, cols, device=g.device, dtype=BF16)
+        ext[:, :patch] = xb.view(B, T // patch, patch, E).transpose(2, 3).reshape(M, patch)
+        ext[:, patch] = 1.0
+        dwb = gemm_tn(g2, ext, name="gemm_patch_embed_dw")                  # [dim, cols] fp32
+        dw = dwb[:, :patch].to(w_dtype)
+        db = None if b_dtype is None else dwb[:, patch].to(b_dtype)
+        return None, dw, db
+
+
+def patch_embed(x, weight, bias=None):
+    """[B, T, E] signal -> [B, (T/p) * E, dim] bf16 tokens, token = (time patch, electrode), = Linear(p -> dim)(to_patches(x))
+    (models/brainformer.py:282-285) without materialising the patch tensor.  x gets no gradient (it is data)."""
+    if x.requires_grad:
+        raise FkError("patch_embed: the input signal is data (no input gradient); use Encoder.embed(to_patches(x)) otherwise")
+    return _PatchEmbedFn.apply(x, weight, bias)

@@ -403,3 +403,92 @@ def attention_qkv(qkv, n_heads: int, rope: Optional[RopeSpec] = None, mask: Opti
     if scale is None:
         scale = hd ** -0.5
     return _AttnQKVFn.apply(qkv, n_heads, rope, mask, scale, rope_applied)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# attention with few queries (perceiver resampler: <= 64 queries, head_dim 16 / 32 / 64, no mask)
+# ------------------------------------------------------------------------------------------------
+SMALL_ATTN_MAX_Q = 64
+
+
+def small_attention_supported(Tq: int, head_dim: int) -> bool:
+    return Tq <= SMALL_ATTN_MAX_Q and head_dim in (16, 32, 64)
+
+
+def _rows_ok(t: torch.Tensor) -> torch.Tensor:
+    """dense bf16 [B, T, W]."""
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    return t.contiguous()           # (gradient buffers share the operands' strides; the tensors here are small or already dense)
+
+
+class _SmallAttnFn(torch.autograd.Function):
+    @staticmethod
+    @on_tensor_device
+    def forward(ctx, q, k, v, n_heads, scale, rope_table, rope_q0, rope_k0):
+        require_cuda(q, k, v)
+        require_device()
+        q, k, v = _rows_ok(q), _rows_ok(k), _rows_ok(v)
+        B, Tq, W = q.shape
+        S = k.shape[1]
+        H = n_heads
+        hd = W // H
+        if k.shape != (B, S, W) or v.shape != (B, S, W):
+            raise FkError(f"small_attention: q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)} do not match")
+        if not small_attention_supported(Tq, hd):
+            raise FkError("small_attention serves <= 64 queries at head_dim 16 / 32 / 64")
+        dev = q.device
+        nch = lib().fk_small_attn_chunks(S)
+        out = torch.empty(B, Tq, W, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, H, Tq, device=dev, dtype=torch.float32)
+        part_o = torch.empty(B, H, nch, Tq, hd, device=dev, dtype=torch.float32)
+        part_ml = torch.empty(B, H, nch, Tq, 2, device=dev, dtype=torch.float32)
+        rl = 0 if rope_table is None else rope_table.shape[0]
+        with timed("small_attn_fwd", 4.0 * B * H * Tq * S * hd):
+            check(lib().fk_small_attn_forward(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v),
+                                              v.stride(0), v.stride(1), ptr(out), out.stride(0), out.stride(1), ptr(lse), B, H,
+                                              Tq, S, hd, scale, ptr(rope_table), rl, rope_q0, rope_k0, ptr(part_o),
+                                              ptr(part_ml), stream()), "fk_small_attn_forward")
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.meta = (H, hd, scale, rope_table, rope_q0, rope_k0, nch)
+        return out
+
+    @staticmethod
+    @on_tensor_device
+    def backward(ctx, g):
+        q, k, v, out, lse = ctx.saved_tensors
+        H, hd, scale, rope_table, rope_q0, rope_k0, nch = ctx.meta
+        B, Tq, W = q.shape
+        S = k.shape[1]
+        g = _rows_ok(g)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        if dk.stride() != k.stride() or dv.stride() != v.stride() or dq.stride() != q.stride():
+            raise FkError("small_attention backward: gradient buffers must share the operands' strides")
+        part_dq = torch.empty(B, H, nch, Tq, hd, device=q.device, dtype=torch.float32)
+        rl = 0 if rope_table is None else rope_table.shape[0]
+        with timed("small_attn_bwd", 10.0 * B * H * Tq * S * hd):
+            check(lib().fk_small_attn_backward(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v),
+                                               v.stride(0), v.stride(1), ptr(out), out.stride(0), out.stride(1), ptr(g),
+                                               g.stride(0), g.stride(1), ptr(lse), ptr(dq), ptr(dk), ptr(dv), B, H, Tq, S, hd,
+                                               scale, ptr(rope_table), rl, rope_q0, rope_k0, ptr(part_dq), stream()),
+                  "fk_small_attn_backward")
+        return dq, dk, dv, None, None, None, None, None
+
+
+def small_attention(q, k, v, n_heads: int, scale: Optional[float] = None, rope: Optional[RopeSpec] = None,
+                    rope_q0: Optional[int] = None, rope_k0: Optional[int] = None):
+    """softmax(q k^T * scale) v for few queries: q [B, Tq <= 64, H*hd], k / v [B, S, H*hd] -> [B, Tq, H*hd] bf16 (no mask).
+    rope: table positions of query t / key j are rope_q0 + t / rope_k0 + j (defaults: the spec's offset for both)."""
+    hd = q.shape[-1] // n_heads
+    if scale is None:
+        scale = hd ** -0.5
+    table = None
+    if rope is not None:
+        if rope.pos is not None:
+            raise FkError("small_attention takes contiguous rope positions only")
+        table = rope.table
+        rope_q0 = rope.offset if rope_q0 is None else rope_q0
+        rope_k0 = rope.offset if rope_k0 is None else rope_k0
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise FkError("frankenstein_b200 kernels run on a B200 only (no CPU fallback)")
+    return _SmallAttnFn.apply(q, k, v, n_heads, float(scale), table, int(rope_q0 or 0), int(rope_k0 or 0))

@@ -227,6 +227,14 @@ int fk_gemm_tn_splits(long long M, int Na, int Nb, int max_ctas);
 int fk_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* out, long long M, int Na, int Nb,
                float* ws, int splits, void* stream);
 
+/* Patch embedding of brainformer.Encoder (brainformer.py:282 to_patches, :285 Linear(patch -> dim) + bias, :343 + electrode
+ * embedding): x bf16 [n_rows = B * T, E] row-major (ldx), token (b, t, c) = x[b*T + t*patch .. + patch, c];
+ * wt = W^T bf16 [patch, dim]; bias fp32 [dim] (nullable); emb fp32 [E, dim] (nullable) added per electrode;
+ * out bf16 [n_rows / patch * E, dim] = token-major 'b (t c) d'.  The [B, S, patch] patch tensor is never materialised: TMA reads
+ * x as the MN-major operand of a tcgen05 contraction over the patch's bins.  patch in {16, 32, 48, 64}, E % 64 == 0, dim % 64 == 0. */
+int fk_patch_embed_forward(const void* x_bf16, long long ldx, const void* wt_bf16, const float* bias, const float* emb,
+                           void* out_bf16, long long n_rows, int E, int patch, int dim, void* stream);
+
 /* ---- input pipeline on the device (utils/data_utils.py) ------------------------------------------------
  * Ragged trials stored back to back: volt [sum_T, C1] fp32 (spike power), spk [sum_T, C2] fp32 (threshold crossings; C2 = 0
  * and spk = null for already concatenated data), offsets [n_trials + 1] int64 first row of each trial, block_id [n_trials]
@@ -247,6 +255,24 @@ int fk_input_block_reduce(const double* part, const long long* offsets, const in
 int fk_input_normalize(const float* volt, const float* spk, const long long* offsets, const int* block_id, const float* mean,
                        const float* stdv, int n_trials, int C1, int C2, int T_out, int smooth, void* out, int out_dtype,
                        void* stream);
+
+/* ---- attention with few queries: the perceiver resampler (brainformer.py:175-219, :247-268) --------------
+ * softmax(q k^T * scale) v for Tq <= 64 queries per (trial, head) against S keys, head_dim 16 / 32 / 64, no mask, bf16
+ * [B, T, H, head_dim] operands with batch / token strides in elements (token strides % 8 == 0).  rope_table (nullable):
+ * [rope_len, head_dim / 2, 2] fp32 (cos, sin); q row t is rotated by position rope_q0 + t, k row j by rope_k0 + j
+ * (apply_rope, brainformer.py:70-91) and dq / dk are rotated back.  The key axis is split into
+ * fk_small_attn_chunks(S) chunks of 256: part_o fp32 [B, H, chunks, Tq, head_dim], part_ml fp32 [B, H, chunks, Tq, 2],
+ * part_dq like part_o; partials are merged in chunk order (deterministic).  lse [B, H, Tq] in the log2 domain. */
+int fk_small_attn_chunks(int S);
+int fk_small_attn_forward(const void* q, long long q_bs, long long q_ts, const void* k, long long k_bs, long long k_ts,
+                          const void* v, long long v_bs, long long v_ts, void* out, long long o_bs, long long o_ts,
+                          float* lse, int B, int H, int Tq, int S, int head_dim, float scale, const float* rope_table,
+                          int rope_len, int rope_q0, int rope_k0, float* part_o, float* part_ml, void* stream);
+int fk_small_attn_backward(const void* q, long long q_bs, long long q_ts, const void* k, long long k_bs, long long k_ts,
+                           const void* v, long long v_bs, long long v_ts, const void* out, long long o_bs, long long o_ts,
+                           const void* dout, long long do_bs, long long do_ts, const float* lse, void* dq, void* dk,
+                           void* dv, int B, int H, int Tq, int S, int head_dim, float scale, const float* rope_table,
+                           int rope_len, int rope_q0, int rope_k0, float* part_dq, void* stream);
 
 /* ---- encoder -> GPT-2 prefix hand-off (models/gpt2_model.py:178-196) -------------------------------------
  * out [B, Tc + T, D] = cat([prefix [B, Tc, D], wte[idx [B, T]]], dim 1) + wpe[0 .. Tc + T); wte [V, D], wpe [P, D] fp32;

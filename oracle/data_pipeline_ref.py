@@ -100,9 +100,14 @@ def pad_truncate_brain_list(brain_list, max_length):
     return out
 
 
-def make_batch(voltage_list, spikes_list, block_list, max_length, smooth=True):
+def make_batch(voltage_list, spikes_list, block_list, max_length, smooth=True, exact=False):
     """process_signal -> pad_truncate_brain_list -> astype(float32) -> stack: the [n, max_length, C] batch the trainer's
-    DataLoader hands to the model (utils/data_utils.py:115-156, :243-267, :335-344)."""
+    DataLoader hands to the model (utils/data_utils.py:115-156, :243-267, :335-344).
+    exact=True evaluates the same formulas in float64 (the reference works in the arrays' own float32, where numpy's
+    axis-0 mean / std add rows one by one: at ~50 k bins per block its statistics carry ~1e-5 relative rounding error)."""
+    if exact:
+        voltage_list = [np.asarray(v, dtype=np.float64) for v in voltage_list]
+        spikes_list = [np.asarray(v, dtype=np.float64) for v in spikes_list]
     if smooth:
         proc = process_signal(voltage_list, spikes_list, block_list)
     else:

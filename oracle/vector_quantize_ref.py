@@ -77,7 +77,7 @@ def kmeans(samples: torch.Tensor, num_clusters: int, num_iters: int, use_cosine_
         all_reduce_fn(bins)
         zero_mask = bins == 0
         bins_min_clamped = bins.masked_fill(zero_mask, 1)
-        new_means = torch.zeros(num_clusters, samples.shape[-1], dtype=samples.dtype)
+        new_means = torch.zeros(num_clusters, samples.shape[-1], dtype=samples.dtype, device=samples.device)
         new_means.index_add_(0, buckets, samples)
         new_means = new_means / bins_min_clamped[:, None]
         all_reduce_fn(new_means)
@@ -190,7 +190,7 @@ class VectorQuantizeRef(nn.Module):
                 bins = torch.bincount(ind, minlength=self.codebook_size).to(f.dtype)
                 self.all_reduce_fn(bins)
                 cb.cluster_size.data[0].lerp_(bins, 1 - self.decay)
-                embed_sum = torch.zeros(self.codebook_size, shape[-1], dtype=f.dtype)
+                embed_sum = torch.zeros(self.codebook_size, shape[-1], dtype=f.dtype, device=f.device)
                 embed_sum.index_add_(0, ind, f)
                 self.all_reduce_fn(embed_sum)
                 cb.embed_avg.data[0].lerp_(embed_sum, 1 - self.decay)
@@ -204,7 +204,7 @@ class VectorQuantizeRef(nn.Module):
 
         quantize = quantize.reshape(shape)
         ind = ind.reshape(shape[:-1])
-        loss = torch.zeros(1, requires_grad=self.training)
+        loss = torch.zeros(1, device=x.device, requires_grad=self.training)
         if self.training:
             commit_quantize = quantize.detach()
             quantize = x + (quantize - x).detach()

@@ -28,6 +28,23 @@ __global__ void __launch_bounds__(512, 1) k(int iters, float* out, long long* cy
         x[i] = x[i] - 0.001f;
       } else if (OP == 3) {
         asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+      } else if (OP == 4) {                     // two half-precision exponentials per instruction
+        unsigned r = __float_as_uint(x[i]);
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r));
+        x[i] = __uint_as_float(r);
+      } else if (OP == 5) {
+        unsigned r = __float_as_uint(x[i]);
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(r));
+        x[i] = __uint_as_float(r);
+      } else if (OP == 6) {                     // the softmax inner step with packed half exponentials:
+        unsigned r;                             // pack two fp32 arguments, one MUFU, (result stays f16x2)
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x[i]), "f"(x[(i + 1) & 7]));
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r));
+        acc ^= r;
+      } else if (OP == 7) {
+        unsigned r;
+        asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(__float_as_uint(x[i])));
+        x[i] = __uint_as_float(r);
       }
     }
   }
@@ -57,5 +74,9 @@ int main() {
   run<1>("F2FP.BF16.PACK_AB", out, cyc);
   run<2>("EX2 + 3 FP32 ops", out, cyc);
   run<3>("MUFU.RCP", out, cyc);
+  run<4>("MUFU.EX2.F16x2 (instructions; x2 results)", out, cyc);
+  run<5>("MUFU.EX2.BF16x2 (instructions; x2 results)", out, cyc);
+  run<6>("cvt.f16x2 + EX2.F16x2 (pairs)", out, cyc);
+  run<7>("MUFU.TANH.F16x2 (instructions; x2 results)", out, cyc);
   return 0;
 }

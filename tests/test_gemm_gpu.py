@@ -164,3 +164,27 @@ def test_linear_qkv_mlp_functions_match_torch(mlp_bwd, monkeypatch):
     close(xr.grad, ref_p[0].grad, 2e-2, "qkv dx")
     for name, a, b in (("dwq", wq, ref_p[1]), ("dwk", wk, ref_p[2]), ("dwv", wv, ref_p[3])):
         close(a.grad, b.grad, 2e-2, f"qkv {name}")
+
+
+@pytest.mark.parametrize("B,T,E,patch,dim", [(2, 64, 64, 32, 128), (3, 96, 128, 48, 64), (2, 512, 256, 32, 512), (1, 64, 192, 16, 320),
+                                             (2, 128, 64, 64, 64)])
+def test_patch_embed_matches_linear_of_to_patches(B, T, E, patch, dim):
+    """fk_patch_embed_forward (TMA-strided patchify + tcgen05 contraction + bias) against F.linear(to_patches(x)) in fp32 on
+    the same bf16-rounded operands (models/brainformer.py:282-285), with dW / db through the split-K TN kernel."""
+    from frankenstein_b200 import gemm
+    g = torch.Generator().manual_seed(T + E)
+    x = torch.randn(B, T, E, generator=g).cuda()
+    w = (torch.randn(dim, patch, generator=g) * patch ** -0.5).cuda().requires_grad_(True)
+    b = (torch.randn(dim, generator=g) * 0.1).cuda().requires_grad_(True)
+    wout = torch.randn(B, (T // patch) * E, dim, generator=g).cuda().to(torch.bfloat16)
+    y = gemm.patch_embed(x, w, b)
+    y.backward(wout)
+    xr = x.to(torch.bfloat16).float()
+    patches = xr.view(B, T // patch, patch, E).transpose(2, 3).reshape(B, (T // patch) * E, patch)
+    w2, b2 = w.detach().to(torch.bfloat16).float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    ref = F.linear(patches, w2, b2)
+    (ref * wout.float()).sum().backward()
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16
+    close(y, ref, 1e-2, "patch embed out")
+    close(w.grad, w2.grad, 2e-2, "patch embed dw")
+    close(b.grad, b2.grad, 2e-2, "patch embed db")

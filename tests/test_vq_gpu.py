@@ -293,6 +293,17 @@ def test_ema_stats_deterministic_and_exact():
     assert torch.allclose(first[:K * D].view(K, D).double(), ref, rtol=1e-5, atol=1e-4)
     assert torch.equal(first[K * D:], torch.bincount(ind, minlength=K).float())
     assert first[K * D + 11] == 0 and (first[11 * D:12 * D] == 0).all()
+    # degenerate assignments: every row on one code (row-scan path, ragged N), and segments right at the path boundaries
+    for N2, K2, make in ((5003, 64, lambda n: torch.full((n,), 5)),
+                         (4000, 8, lambda n: torch.cat([torch.zeros(32), torch.ones(33), torch.full((1024,), 2), torch.full((1025,), 3),
+                                                        torch.full((n - 2114,), 4)]))):
+        x2 = torch.randn(N2, 64, generator=g).cuda()
+        i2 = make(N2).long()[torch.randperm(N2, generator=g)].cuda()
+        s2 = fvq.ema_stats(x2, i2, K2)
+        assert torch.equal(fvq.ema_stats(x2, i2, K2), s2)
+        ref2 = torch.zeros(K2, 64, dtype=torch.float64, device="cuda").index_add_(0, i2, x2.double())
+        assert torch.allclose(s2[:K2 * 64].view(K2, 64).double(), ref2, rtol=1e-5, atol=1e-3)
+        assert torch.equal(s2[K2 * 64:], torch.bincount(i2, minlength=K2).float())
 
 
 @pytest.mark.parametrize("cosine", [False, True])
