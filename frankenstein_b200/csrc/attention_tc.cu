@@ -53,6 +53,8 @@ struct TcParams {
   long long* prof;                                     // kProf instantiation: [n_ctas][16] cycle counters
   unsigned int* items;                                 // caller-owned hand-out counters of THIS launch: [0] next item,
                                                        // [1] CTAs finished; zero on entry, zeroed again by the last CTA out
+  int fold;                                            // 1: lse and delta arrive as an extra K step of the score MMAs (tm_aug):
+                                                       //    S' = S - lse / c, dP' = dP - delta come out of the tensor core
   int mn_major;                                        // 1: the accumulate MMAs read their B operand (Q / dO / K tile,
                                                        // [64 tokens][32 dims]) MN-major from the score stage itself;
                                                        // 0: K-major from transposed copies (tm_tA / tm_tB)
@@ -83,8 +85,12 @@ struct TcSmem {
   static constexpr int stream = 32768;                 // kNST x 16 KB: stA | stB | tA | tB (4 KB each)
   static constexpr int stats = stream + kNST * 16384;  // [2 wg][2 buffers][lse | delta | id][64] x 4 B           // [2 wg][lse | delta | id][64] x 4 B
   static constexpr int tiles = stats + kNG * 2 * 3 * 64 * 4; // uint16 visible-tile list
-  static constexpr int bars = tiles + 2 * kMaxTiles * 2;   // two lists: the next item's is built while this one runs
-  static constexpr int total = bars + 256;
+  // folded statistics (TcParams::fold): two constant [128][16] operand tiles (ones in columns 0-2 / 3-5) and, for the dQ
+  // kernel, the resident queries' statistics rows (two buffers, like the resident tiles); 32-byte rows, SWIZZLE_32B
+  static constexpr int ones = (tiles + 2 * kMaxTiles * 2 + 1023) / 1024 * 1024;   // two lists: the next item's is built while this one runs
+  static constexpr int aug_res = ones + 8192;
+  static constexpr int bars = aug_res + 8192;
+  static constexpr int total = bars + 512;
 };
 
 // FK_ATTN_EXP (diagnosis builds only, results are WRONG): 1 = no MUFU, 2 = no TMEM operand stores, 3 = no stats LDS,
@@ -165,11 +171,12 @@ __device__ __forceinline__ void tmem_wait1_32(uint32_t (&a)[32]) {
 // to the caller (one pair per launch in flight: launches on different streams must be given different pairs), so the
 // library holds no device-side state and is re-entrant per stream.
 
-template <int MODE, int kProf>
+template <int MODE, int kProf, bool kFold>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_constant__ CUtensorMap tm_resB,
                    const __grid_constant__ CUtensorMap tm_stA, const __grid_constant__ CUtensorMap tm_stB,
-                   const __grid_constant__ CUtensorMap tm_tA, const __grid_constant__ CUtensorMap tm_tB, const TcParams p) {
+                   const __grid_constant__ CUtensorMap tm_tA, const __grid_constant__ CUtensorMap tm_tB,
+                   const __grid_constant__ CUtensorMap tm_aug, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);
@@ -181,9 +188,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   uint64_t* stage_free = sdp_full + kNG;   // [kNG]  the accumulate MMAs that read stage g (as P / dS) have retired
   uint64_t* p_ready = stage_free + kNG;    // [kNG]  P / dS written in place into stage g (4 warps arrive)
   uint64_t* acc_full = p_ready + kNG;      // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  int* n_tiles_slot = reinterpret_cast<int*>(acc_full + 1) + 1;   // [2]
-  int* item_slot = reinterpret_cast<int*>(acc_full + 1) + 3;      // [2]: item ids handed to this CTA, double buffered
+  uint64_t* dp_full = acc_full + 1;        // [kNG]  fold: dP of stage g written (sdp_full then announces S alone, so the
+                                           //        exponentials of a tile start while its dP MMAs still run)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dp_full + kNG);
+  int* n_tiles_slot = reinterpret_cast<int*>(dp_full + kNG) + 1;   // [2]
+  int* item_slot = reinterpret_cast<int*>(dp_full + kNG) + 3;      // [2]: item ids handed to this CTA, double buffered
   uint16_t* tile_lists = reinterpret_cast<uint16_t*>(smem + TcSmem::tiles);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,6 +217,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       mbar_init(&sdp_full[i], 1);
       mbar_init(&stage_free[i], 1);
       mbar_init(&p_ready[i], 4);
+      mbar_init(&dp_full[i], 1);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -215,6 +225,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
+  }
+  constexpr bool fold = kFold;                     // (compile time: the folded and the staged hot loops share no registers)
+  if (fold && warp >= 4) {
+    // constant operand tiles of the statistics K step: row r = 16 bf16, ones in columns 0-2 (picks -lse / c) resp. 3-5
+    // (picks -delta), written in the SWIZZLE_32B pattern (the two 16-byte halves of a row swap when bit 2 of r is set)
+    for (int i = threadIdx.x - 128; i < 2 * 128 * 2; i += kTcThreads - 128) {
+      const int tile = i >> 8, r = (i >> 1) & 127, pc = i & 1;
+      const int c = pc ^ ((r >> 2) & 1);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (c == 0) v = tile == 0 ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0x3F800000u, 0x3F803F80u, 0u);
+      *reinterpret_cast<uint4*>(smem + TcSmem::ones + tile * 4096 + r * 32 + pc * 16) = v;
+    }
+    fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core's (async proxy) reads
   }
   tc_fence_before();
   __syncthreads();
@@ -311,9 +334,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       long long w_se = 0;
       auto load_resident = [&](int h_, int r0_, int b_, int buf) {
         if (elect_one()) {
-          mbar_expect_tx(&res_full[buf], 16384);
+          mbar_expect_tx(&res_full[buf], (MODE == MODE_DQ && fold) ? 16384u + 4096u : 16384u);
           tma_load_4d(smem + TcSmem::resA + buf * 16384, &tm_resA, &res_full[buf], 0, h_, r0_, b_);
           tma_load_4d(smem + TcSmem::resB + buf * 16384, &tm_resB, &res_full[buf], 0, h_, r0_, b_);
+          if (MODE == MODE_DQ && fold) tma_load_4d(smem + TcSmem::aug_res + buf * 4096, &tm_aug, &res_full[buf], 0, r0_, h_, b_);
         }
         __syncwarp();
       };
@@ -321,9 +345,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         uint8_t* st = smem + TcSmem::stream + pstage * 16384;
         wait_acc<kProf>(&st_empty[pstage], pphase ^ 1, w_se);
         if (elect_one()) {
-          mbar_expect_tx(&st_full[pstage], p.mn_major ? 8192u : kStageBytes);
+          mbar_expect_tx(&st_full[pstage], p.mn_major ? ((MODE == MODE_DKV && fold) ? 8192u + 2048u : 8192u) : kStageBytes);
           tma_load_4d(st, &tm_stA, &st_full[pstage], 0, h_, t * kCols, b_);
           tma_load_4d(st + 4096, &tm_stB, &st_full[pstage], 0, h_, t * kCols, b_);
+          if (MODE == MODE_DKV && fold) tma_load_4d(st + 8192, &tm_aug, &st_full[pstage], 0, t * kCols, h_, b_);   // statistics rows of the tile's queries
           if (!p.mn_major) {
             if (MODE == MODE_DKV) tma_load_2d(st + 8192, &tm_tA, &st_full[pstage], t * kCols, (b_ * p.H + h_) * 32);
             tma_load_2d(st + 12288, &tm_tB, &st_full[pstage], t * kCols, (b_ * p.H + h_) * 32);
@@ -374,6 +399,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         uint64_t dS = umma_desc_sw64(stream + stage * 16384), dD = umma_desc_sw64(stream + stage * 16384 + 4096);
         uint32_t d_s = tmem_u + g * 128, d_dp = tmem_u + g * 128 + 64;
         uint64_t* const bar_full = &sdp_full[g];
+        // statistics K step (fold): DKV  A = constant ones tile (keys), B = the tile's query statistics;
+        //                           DQ   A = the resident queries' statistics, B = constant ones tile (keys)
+        uint64_t fA_s = 0, fA_d = 0, fB_s = 0, fB_d = 0;
+        if constexpr (fold) {
+          fA_s = umma_desc_sw32(smem_u32(smem + TcSmem::ones));
+          fA_d = umma_desc_sw32(smem_u32(smem + TcSmem::ones + 4096));
+          fB_s = fB_d = umma_desc_sw32(stream + stage * 16384 + 8192);
+          if (MODE == MODE_DQ) {
+            fB_s = fA_s; fB_d = fA_d;
+            fA_s = fA_d = umma_desc_sw32(smem_u32(smem + TcSmem::aug_res + (item_n & 1) * 4096));
+          }
+          asm volatile("" : "+l"(fA_s), "+l"(fA_d), "+l"(fB_s), "+l"(fB_d));
+        }
         {
           // pin the values here: without this the compiler sinks the whole address arithmetic below the waits again
           asm volatile("" : "+l"(dS), "+l"(dD), "+r"(d_s), "+r"(d_dp));
@@ -386,9 +424,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
           // a K step of 16 bf16 = 32 bytes = +2 in the descriptor's (address >> 4) field
           umma_bf16(d_s, dA, dS, idesc_score, 0u);
           umma_bf16(d_s, dA + 2, dS + 2, idesc_score, 1u);
+          if (fold) {
+            umma_bf16(d_s, fA_s, fB_s, idesc_score, 1u);
+            umma_commit(bar_full);                         // S' complete: the warpgroup starts on the exponentials
+          }
           umma_bf16(d_dp, dB, dD, idesc_score, 0u);
           umma_bf16(d_dp, dB + 2, dD + 2, idesc_score, 1u);
-          umma_commit(bar_full);
+          if (fold) {
+            umma_bf16(d_dp, fA_d, fB_d, idesc_score, 1u);
+            umma_commit(&dp_full[g]);
+          } else {
+            umma_commit(bar_full);
+          }
         }
         __syncwarp();
         if (kFull && trace && lane == 0 && js < 128) trace[3 * 128 + js] = clock64();
@@ -464,7 +511,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
                                        : (MODE == MODE_DKV ? 0x7fffffff : -0x7fffffff))
                              : 0;
     float my_lse = INFINITY, my_delta = 0.f;     // DQ: per-row statistics
-    if (MODE == MODE_DQ && row_ok) { my_lse = lse_g[row]; my_delta = delta_g[row]; }
+    if (MODE == MODE_DQ && row_ok && !fold) { my_lse = lse_g[row]; my_delta = delta_g[row]; }
 
     // column statistics of a streamed tile, fetched one own-tile ahead
     float pre_f = 0.f;
@@ -473,6 +520,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       if (j >= T) return;
       const int c = (tile_list[j] & 0x7fff) * kCols + (tid & 63);
       const bool ok = c < p.S_col;
+      if (fold) {
+        // only the labels are still needed, and only by tiles that straddle a label boundary
+        if ((tile_list[j] & 0x8000) && tid < 64)
+          pre_i = ok ? (masked ? p.col_id[static_cast<long long>(b) * p.S_col + c] : 0) : (MODE == MODE_DKV ? -0x7fffffff : 0x7fffffff);
+        return;
+      }
       if (MODE == MODE_DKV) {
         if (tid < 64) {
           pre_f = ok ? lse_g[c] : INFINITY;
@@ -497,14 +550,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       float* s_delta = s_lse + 64;
       int* s_id = reinterpret_cast<int*>(s_lse + 128);
 #if FK_ATTN_EXP != 7
-      if (MODE == MODE_DKV) {
-        if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else { s_delta[tid - 64] = pre_f; }
-      } else if (tid < 64) {
-        s_id[tid] = pre_i;
+      if (fold) {
+        // no per-tile staging: the statistics come out of the score MMAs.  Labels only for boundary tiles (two barriers:
+        // the buffer is shared by consecutive masked tiles of this warpgroup)
+        if (need_mask) {
+          named_bar_sync(1 + g, 128);
+          if (tid < 64) s_id[tid] = pre_i;
+          named_bar_sync(1 + g, 128);
+        }
+      } else {
+        if (MODE == MODE_DKV) {
+          if (tid < 64) { s_lse[tid] = pre_f; s_id[tid] = pre_i; } else { s_delta[tid - 64] = pre_f; }
+        } else if (tid < 64) {
+          s_id[tid] = pre_i;
+        }
+        const long long tb0 = kFull ? clock64() : 0;
+        named_bar_sync(1 + g, 128);
+        if (kFull) w_bar += clock64() - tb0;
       }
-      const long long tb0 = kFull ? clock64() : 0;
-      named_bar_sync(1 + g, 128);
-      if (kFull) w_bar += clock64() - tb0;
       prefetch(j + kNG);
 #endif
       wait_acc<kProf>(&sdp_full[g], n & 1, w_full);
@@ -517,6 +580,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       // sub-chunk i is computed and its bf16 pairs are stored over columns this thread has already consumed
       // (sub-chunk i occupies fp32 columns 16 i .. 16 i + 15, its pairs go to 8 i .. 8 i + 7)
       uint32_t sv[2][16], dv[2][16];
+      if constexpr (fold) {
+        // folded statistics: sv = S - lse / c and dv = dP - delta leave the tensor core.  P of sub-chunk i + 1 is formed
+        // one step ahead, and the first one before dP is even waited for (its MMAs run behind the S MMAs).
+        float pf[16];
+        auto expo = [&](uint32_t (&s16)[16], int i) {
+          if (need_mask) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int cid = s_id[i * 16 + e];
+              const bool hide = (MODE == MODE_DKV) ? (my_id > cid) : (cid > my_id);
+              if (hide) s16[e] = 0xff800000u;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pf[e] = fast_ex2(__uint_as_float(s16[e]) * p.scale_log2);
+        };
+        tmem_ld16(taddr, sv[0]);
+        tmem_wait1_16(sv[0]);
+        tmem_ld16(taddr + 16, sv[1]);
+        expo(sv[0], 0);
+        mbar_wait(&dp_full[g], n & 1);
+        tc_fence_after();
+        tmem_ld16(taddr + 64, dv[0]);
+#pragma unroll
+        for (int i = 0; i < kSub; ++i) {
+          const int cur = i & 1;
+          if (i < kSub - 1) tmem_wait2_16(dv[cur], sv[cur ^ 1]); else tmem_wait1_16(dv[cur]);
+          if (i < kSub - 1) tmem_ld16(taddr + 64 + (i + 1) * 16, dv[cur ^ 1]);
+          if (i < kSub - 2) tmem_ld16(taddr + (i + 2) * 16, sv[cur]);
+          uint32_t pw[8], dw[8];
+#pragma unroll
+          for (int e2 = 0; e2 < 8; ++e2) {
+            const float s0 = pf[2 * e2] * __uint_as_float(dv[cur][2 * e2]);
+            const float s1 = pf[2 * e2 + 1] * __uint_as_float(dv[cur][2 * e2 + 1]);
+            if (MODE == MODE_DKV) pw[e2] = pack2(pf[2 * e2], pf[2 * e2 + 1]);
+            dw[e2] = pack2(s0, s1);
+          }
+          if (MODE == MODE_DKV) tmem_st8(taddr + i * 8, pw);
+          tmem_st8(taddr + 64 + i * 8, dw);
+          if (i < kSub - 1) expo(sv[cur ^ 1], i + 1);
+        }
+      } else {
       tmem_ld16(taddr, sv[0]);
       tmem_ld16(taddr + 64, dv[0]);
 #pragma unroll
@@ -539,7 +644,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
           float lse8[8], dl8[8];
-          if (MODE == MODE_DKV && FK_ATTN_EXP != 3 && FK_ATTN_EXP != 7) {
+          if (MODE == MODE_DKV && !fold && FK_ATTN_EXP != 3 && FK_ATTN_EXP != 7) {
             const float4 l0 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8);
             const float4 l1 = *reinterpret_cast<const float4*>(s_lse + i * 16 + g8 * 8 + 4);
             const float4 d0 = *reinterpret_cast<const float4*>(s_delta + i * 16 + g8 * 8);
@@ -565,15 +670,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
             const float p0 = fast_ex2(__uint_as_float(sv[cur][i0]));
             const float p1 = fast_ex2(__uint_as_float(sv[cur][i0 + 1]));
 #else
-            const float p0 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0]), p.scale_log2, -lse8[e2 * 2]));
-            const float p1 = fast_ex2(fmaf(__uint_as_float(sv[cur][i0 + 1]), p.scale_log2, -lse8[e2 * 2 + 1]));
+            // fold: sv = S - lse / c  ->  P = 2^(c sv); otherwise P = 2^(c S - lse)
+            const float p0 = fast_ex2(fold ? __uint_as_float(sv[cur][i0]) * p.scale_log2
+                                           : fmaf(__uint_as_float(sv[cur][i0]), p.scale_log2, -lse8[e2 * 2]));
+            const float p1 = fast_ex2(fold ? __uint_as_float(sv[cur][i0 + 1]) * p.scale_log2
+                                           : fmaf(__uint_as_float(sv[cur][i0 + 1]), p.scale_log2, -lse8[e2 * 2 + 1]));
 #endif
 #if FK_ATTN_EXP == 5 || FK_ATTN_EXP == 6 || FK_ATTN_EXP == 7
             const float s0 = p0 * __uint_as_float(dv[cur][i0]);           // what folding delta into the dP MMA would leave
             const float s1 = p1 * __uint_as_float(dv[cur][i0 + 1]);
 #else
-            const float s0 = p0 * (__uint_as_float(dv[cur][i0]) - dl8[e2 * 2]);
-            const float s1 = p1 * (__uint_as_float(dv[cur][i0 + 1]) - dl8[e2 * 2 + 1]);
+            // fold: dv = dP - delta already
+            const float s0 = p0 * (fold ? __uint_as_float(dv[cur][i0]) : __uint_as_float(dv[cur][i0]) - dl8[e2 * 2]);
+            const float s1 = p1 * (fold ? __uint_as_float(dv[cur][i0 + 1]) : __uint_as_float(dv[cur][i0 + 1]) - dl8[e2 * 2 + 1]);
 #endif
             if (MODE == MODE_DKV) pw[g8 * 4 + e2] = pack2(p0, p1);
             dw[g8 * 4 + e2] = pack2(s0, s1);
@@ -587,6 +696,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         tmem_st8(taddr + 64 + i * 8, dw);
 #endif
       }
+      }   // staged statistics
 #if FK_ATTN_EXP == 8
       // cost probe for a single-pass backward: the dQ partial of this tile ([64 queries x 32] fp32) reduced into global
       // memory with vector reds, 4 per thread (targets: the dV / dK output rows of the tile's queries -- results are WRONG)
@@ -687,6 +797,55 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       __threadfence();
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row statistics of the backward as tensor-core operands: delta[b,h,i] = sum_d dO O (as attn_delta_kernel) and the
+// statistics row aug[b][h][i][16] (bf16) = (-lse / c split into three bf16 terms | -delta split into three | 0 ...): the
+// score MMAs of the backward kernels take it as one more K step, so that S - lse / c and dP - delta leave the tensor core
+// ready for P = 2^(c (S - lse / c)) and dS = P (dP - delta).  Three bf16 terms carry 24 mantissa bits.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split3(float x, float& hi, float& mid, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(x));
+  const float r1 = x - hi;
+  mid = __bfloat162float(__float2bfloat16_rn(r1));
+  lo = __bfloat162float(__float2bfloat16_rn(r1 - mid));
+}
+
+__global__ void __launch_bounds__(256)
+attn_aug_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse,
+                float* __restrict__ delta, __nv_bfloat16* __restrict__ aug, int B, int H, int S, long long o_bs, long long o_ts,
+                long long do_bs, long long do_ts, float inv_scale_log2) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // (b, i, h)
+  if (idx >= static_cast<long long>(B) * S * H) return;
+  const int h = static_cast<int>(idx % H);
+  const long long bi = idx / H;
+  const int i = static_cast<int>(bi % S), b = static_cast<int>(bi / S);
+  const uint4* op = reinterpret_cast<const uint4*>(o + b * o_bs + static_cast<long long>(i) * o_ts + h * 32);
+  const uint4* dp = reinterpret_cast<const uint4*>(d_o + b * do_bs + static_cast<long long>(i) * do_ts + h * 32);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 a = op[c], e = dp[c];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ew[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      acc += __uint_as_float(aw[j] << 16) * __uint_as_float(ew[j] << 16) +
+             __uint_as_float(aw[j] & 0xffff0000u) * __uint_as_float(ew[j] & 0xffff0000u);
+  }
+  const long long row = (static_cast<long long>(b) * H + h) * S + i;
+  delta[row] = acc;
+  // a row with no visible key has lse = +inf: a large finite value keeps the three-term split free of inf - inf
+  const float l = lse[row];
+  const float nl = (l < 3.0e38f) ? -l * inv_scale_log2 : -1.0e30f;
+  float v[6];
+  split3(nl, v[0], v[1], v[2]);
+  split3(-acc, v[3], v[4], v[5]);
+  uint4 w;
+  w.x = pack2(v[0], v[1]); w.y = pack2(v[2], v[3]); w.z = pack2(v[4], v[5]); w.w = 0u;
+  uint4* dst = reinterpret_cast<uint4*>(aug + row * 16);
+  dst[0] = w;
+  dst[1] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1201,14 +1360,14 @@ static int bwd_sm_count() { return fk_sm_count(); }
 
 // parts: 2 = dK/dV (needs qt, dot), 4 = dQ (needs kt).  delta must already hold rowsum(dO * O) (fk_attn_backward parts=1).
 FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
-                               const void* dot, int Sp, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+                               const void* dot, int Sp, const float* lse, const float* delta, const void* aug, void* dq, void* dk, void* dv,
                                int B, int H, int S, int head_dim, long long q_bs, long long q_ts, long long k_bs,
                                long long k_ts, long long v_bs, long long v_ts, long long do_bs, long long do_ts,
                                long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
                                long long dv_ts, const int* qid, const int* kid, const int* qmin, const int* qmax,
                                const int* kmin, const int* kmax, float scale, const float* rope_table, int rope_len,
                                const int* rope_pos, int rope_offset, int parts, unsigned int* counters, void* stream_) {
-  return fk_attn_backward_tc_profile(q, k, v, d_o, qt, kt, dot, Sp, lse, delta, dq, dk, dv, B, H, S, head_dim, q_bs, q_ts, k_bs,
+  return fk_attn_backward_tc_profile(q, k, v, d_o, qt, kt, dot, Sp, lse, delta, aug, dq, dk, dv, B, H, S, head_dim, q_bs, q_ts, k_bs,
                                      k_ts, v_bs, v_ts, do_bs, do_ts, dq_bs, dq_ts, dk_bs, dk_ts, dv_bs, dv_ts, qid, kid, qmin,
                                      qmax, kmin, kmax, scale, rope_table, rope_len, rope_pos, rope_offset, parts, counters,
                                      nullptr, 0, stream_);
@@ -1217,7 +1376,7 @@ FK_API int fk_attn_backward_tc(const void* q, const void* k, const void* v, cons
 // Same launch; prof != NULL selects the stall-accounting instantiation (diagnosis only, scripts/gpu_attn_stalls.py):
 // prof_mode 1 = full stall accounting, 2 = light (lifetime + global timestamps + SM id).
 FK_API int fk_attn_backward_tc_profile(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
-                               const void* dot, int Sp, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+                               const void* dot, int Sp, const float* lse, const float* delta, const void* aug, void* dq, void* dk, void* dv,
                                int B, int H, int S, int head_dim, long long q_bs, long long q_ts, long long k_bs,
                                long long k_ts, long long v_bs, long long v_ts, long long do_bs, long long do_ts,
                                long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
@@ -1238,12 +1397,14 @@ FK_API int fk_attn_backward_tc_profile(const void* q, const void* k, const void*
   static bool attr_set_dev[FK_MAX_DEVICES];
   bool& attr_set = attr_set_dev[fk_device_ordinal()];
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DKV, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE_DQ, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total) != cudaSuccess) {
       fk_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed", __FILE__, __LINE__);
       return FK_ERR_CUDA;
     }
@@ -1263,6 +1424,15 @@ FK_API int fk_attn_backward_tc_profile(const void* q, const void* k, const void*
   // qt / kt / dot all null: the accumulate MMAs take their B operand MN-major from the [tokens][32] tiles (no copies)
   const int mn_major = (qt == nullptr && kt == nullptr && dot == nullptr) ? 1 : 0;
   mQt = mQ64; mDOt = mDO64; mKt = mK64;
+  // aug (nullable): statistics rows from fk_attn_aug -> lse / delta folded into the score MMAs (needs the MN-major mode:
+  // the statistics tile takes the place of the transposed operand in the streamed stage)
+  const int fold = (aug != nullptr && mn_major && g_attn_prof == nullptr) ? 1 : 0;      // (the stall-accounting builds are staged)
+  CUtensorMap mAug64 = mQ64, mAug128 = mQ64;
+  if (fold) {
+    FK_REQUIRE((reinterpret_cast<uintptr_t>(aug) & 31) == 0, "fk_attn_backward_tc: aug must be 32-byte aligned");
+    rc |= make_tmap_aug_sw32(&mAug64, aug, B, S, H, kCols);
+    rc |= make_tmap_aug_sw32(&mAug128, aug, B, S, H, kRows);
+  }
   if ((parts & 2) && !mn_major) {
     FK_REQUIRE(qt && dot && dk && dv, "fk_attn_backward_tc: dK/dV needs qt, dot, dk, dv");
     rc |= make_tmap_bf16_sw128(&mQt, qt, trows, static_cast<uint64_t>(Sp), 32);
@@ -1290,10 +1460,12 @@ FK_API int fk_attn_backward_tc_profile(const void* q, const void* k, const void*
     p.prof = g_attn_prof;
     p.items = counters;
     p.mn_major = mn_major;
+    p.fold = fold;
     p.rope_table = reinterpret_cast<const float2*>(rope_table); p.rope_pos = rope_pos; p.rope_len = rope_len; p.rope_offset = rope_offset;
-    if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DKV, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
-    else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DKV, 1><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
-    else attn_bwd_tc_kernel<MODE_DKV, 0><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, p);
+    if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DKV, 2, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, mAug64, p);
+    else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DKV, 1, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, mAug64, p);
+    else if (fold) attn_bwd_tc_kernel<MODE_DKV, 0, true><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, mAug64, p);
+    else attn_bwd_tc_kernel<MODE_DKV, 0, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mK128, mV128, mQ64, mDO64, mDOt, mQt, mAug64, p);
     FK_CHECK_LAUNCH();
     ++n;
   }
@@ -1306,14 +1478,33 @@ FK_API int fk_attn_backward_tc_profile(const void* q, const void* k, const void*
     p.prof = g_attn_prof;
     p.items = counters + 2;
     p.mn_major = mn_major;
+    p.fold = fold;
     p.rope_table = reinterpret_cast<const float2*>(rope_table); p.rope_pos = rope_pos; p.rope_len = rope_len; p.rope_offset = rope_offset;
-    if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DQ, 2><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
-    else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DQ, 1><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
-    else attn_bwd_tc_kernel<MODE_DQ, 0><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, p);
+    if (g_attn_prof && g_attn_prof_mode == 2) attn_bwd_tc_kernel<MODE_DQ, 2, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, mAug128, p);
+    else if (g_attn_prof) attn_bwd_tc_kernel<MODE_DQ, 1, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, mAug128, p);
+    else if (fold) attn_bwd_tc_kernel<MODE_DQ, 0, true><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, mAug128, p);
+    else attn_bwd_tc_kernel<MODE_DQ, 0, false><<<grid, kTcThreads, TcSmem::total, stream>>>(mQ128, mDO128, mK64, mV64, mKt, mKt, mAug128, p);
     FK_CHECK_LAUNCH();
     ++n;
   }
   fk_count_launch(n);
+  return FK_OK;
+}
+
+// delta = rowsum(dO * O) and the statistics rows the folded backward takes (see attn_aug_kernel): o / d_o bf16 [B, S, H, 32]
+// with strides in elements, lse fp32 [B, H, S] (log2 domain, from the forward), delta fp32 [B, H, S], aug bf16 [B, H, S, 16].
+FK_API int fk_attn_aug(const void* o, const void* d_o, const float* lse, float* delta, void* aug, int B, int H, int S,
+                       long long o_bs, long long o_ts, long long do_bs, long long do_ts, float scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FK_REQUIRE(o && d_o && lse && delta && aug && B > 0 && H > 0 && S > 0 && scale > 0.f, "fk_attn_aug: bad argument");
+  FK_REQUIRE(o_ts % 8 == 0 && do_ts % 8 == 0 && o_bs % 8 == 0 && do_bs % 8 == 0, "fk_attn_aug: strides must keep 16-byte alignment");
+  FK_REQUIRE((reinterpret_cast<uintptr_t>(aug) & 31) == 0, "fk_attn_aug: aug must be 32-byte aligned");
+  const long long n = static_cast<long long>(B) * S * H;
+  attn_aug_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), lse, delta, static_cast<__nv_bfloat16*>(aug), B, H, S,
+      o_bs, o_ts, do_bs, do_ts, 1.f / (scale * 1.4426950408889634f));
+  FK_CHECK_LAUNCH();
+  fk_count_launch();
   return FK_OK;
 }
 

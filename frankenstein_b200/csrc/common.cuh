@@ -269,6 +269,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
   return d;
 }
 
+// Same for rows of 16 bf16 (32 B) written by TMA with CU_TENSOR_MAP_SWIZZLE_32B (one K step per tile): 8-row groups are
+// 256 B apart, layout type 6 = SWIZZLE_32B; the tile must be 256-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both
 // operands K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {

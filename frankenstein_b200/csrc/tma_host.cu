@@ -70,4 +70,13 @@ int make_tmap_heads_sw64(CUtensorMap* map, const void* base, int B, int S, int H
   return make_tmap_bf16(map, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+// [B][H][S][16] bf16 rows of 32 bytes (the statistics operand of the attention backward): box = box_rows x 16 elements of
+// one (trial, head), 32-byte swizzle
+int make_tmap_aug_sw32(CUtensorMap* map, const void* base, int B, int S, int H, uint32_t box_rows) {
+  const uint64_t dims[4] = {16, static_cast<uint64_t>(S), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {32, static_cast<uint64_t>(S) * 32, static_cast<uint64_t>(S) * H * 32};
+  const uint32_t box[4] = {16, box_rows, 1, 1};
+  return make_tmap_bf16(map, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 }  // namespace fk

@@ -26,6 +26,7 @@ int make_tmap_bf16_chunks(CUtensorMap* map, const void* base, uint64_t rows, uin
 
 // bf16 [B][S][H][32] with token / batch strides (elements): box = one head's 32 columns x box_rows tokens,
 // 64-byte swizzle.  Coordinates: (0, head, token, batch).
+int make_tmap_aug_sw32(CUtensorMap* map, const void* base, int B, int S, int H, uint32_t box_rows);
 int make_tmap_heads_sw64(CUtensorMap* map, const void* base, int B, int S, int H, long long batch_stride,
                          long long token_stride, uint32_t box_rows);
 

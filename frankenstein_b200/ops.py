@@ -23,6 +23,9 @@ ATTN_FWD_IMPL = os.environ.get("FK_ATTN_FWD", "tc")
 # B operand of the backward accumulate MMAs: "mn" = MN-major straight from the [tokens][32] tiles (no copies),
 # "transposed" = K-major from token-contiguous copies made by fk_attn_transpose (cross-check path)
 ATTN_BWD_OPERANDS = os.environ.get("FK_ATTN_BWD_OPERANDS", "mn")
+# row statistics of the backward: "folded" = -lse / c and -delta enter the score MMAs as one more K step (fk_attn_aug),
+# "staged" = read from lse / delta and subtracted by the compute warps (cross-check path)
+ATTN_BWD_STATS = os.environ.get("FK_ATTN_BWD_STATS", "folded")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -352,7 +355,17 @@ class _AttnQKVFn(torch.autograd.Function):
                                              dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
                                              *common, part, stream()), "fk_attn_backward")
 
-        legacy("attn_delta", 1)
+        fold = ATTN_BWD_IMPL != "legacy" and ATTN_BWD_OPERANDS != "transposed" and ATTN_BWD_STATS == "folded"
+        aug = None
+        if fold:
+            # delta and the statistics rows the score MMAs take as one more K step (lse / delta folded into the tensor core)
+            aug = torch.empty(B, H, S, 16, device=qkv.device, dtype=torch.bfloat16)
+            d4a = d_o.view(B, S, H, hd)
+            with timed("attn_delta", 0.0):
+                check(lib().fk_attn_aug(ptr(out), ptr(d4a), ptr(lse), ptr(delta), ptr(aug), B, H, S, out.stride(0), out.stride(1),
+                                        d4a.stride(0), d4a.stride(1), float(ctx.scale), stream()), "fk_attn_aug")
+        else:
+            legacy("attn_delta", 1)
         rope_done = False
         r = ctx.rope
         rope_args = (ptr(r.table), r.table.shape[0], ptr(r.pos), r.offset) if r is not None else (0, 0, 0, 0)
@@ -377,7 +390,7 @@ class _AttnQKVFn(torch.autograd.Function):
                 if part not in _BWD_PARTS:
                     continue
                 args = (ptr(q), ptr(k), ptr(v), ptr(d4), ptr(tr["q"]), ptr(tr["k"]), ptr(tr["do"]), Sp,
-                        ptr(lse), ptr(delta), ptr(dq), ptr(dk), ptr(dv), B, H, S, hd,
+                        ptr(lse), ptr(delta), ptr(aug), ptr(dq), ptr(dk), ptr(dv), B, H, S, hd,
                         q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                         d4.stride(0), d4.stride(1), dq.stride(0), dq.stride(1), dk.stride(0),
                         dk.stride(1), dv.stride(0), dv.stride(1), *common, *rope_args, part, counters(_lib.CTR_ATTN_BWD))

@@ -158,8 +158,14 @@ int fk_attn_backward(const void* q, const void* k, const void* v, const void* o,
  * be given different words.  The library itself holds no device-side state: every entry point is re-entrant per stream. */
 int fk_attn_transpose(const void* x, long long bs, long long ts, int B, int S, int H, int head_dim, void* xt, int Sp,
                       void* stream);
+/* fk_attn_aug: delta [B,H,S] = rowsum(dO * O) and the statistics rows aug (bf16 [B,H,S,16], 32-byte aligned): -lse / c
+ * and -delta as three bf16 terms each.  Passed to fk_attn_backward_tc as `aug` (nullable), they enter the score MMAs as one
+ * more K step, so S - lse / c and dP - delta leave the tensor core and the compute warps neither stage nor subtract the
+ * statistics (aug = NULL: the statistics are read from lse / delta as before). */
+int fk_attn_aug(const void* o, const void* d_o, const float* lse, float* delta, void* aug, int B, int H, int S,
+                long long o_bs, long long o_ts, long long do_bs, long long do_ts, float scale, void* stream);
 int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void* d_o, const void* qt, const void* kt,
-                        const void* dot, int Sp, const float* lse, const float* delta, void* dq, void* dk, void* dv,
+                        const void* dot, int Sp, const float* lse, const float* delta, const void* aug, void* dq, void* dk, void* dv,
                         int B, int H, int S, int head_dim, long long q_bs, long long q_ts, long long k_bs,
                         long long k_ts, long long v_bs, long long v_ts, long long do_bs, long long do_ts,
                         long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts, long long dv_bs,
@@ -173,8 +179,8 @@ int fk_attn_backward_tc(const void* q, const void* k, const void* v, const void*
  * int64 [n_items, 24] cycle counters to prof (see attention_tc.cu); prof_mode 1 = full stall accounting, 2 = lifetime +
  * %globaltimer + %smid only.  prof == NULL behaves exactly like fk_attn_backward_tc. */
 int fk_attn_backward_tc_profile(const void* q, const void* k, const void* v, const void* d_o, const void* qt,
-                                const void* kt, const void* dot, int Sp, const float* lse, const float* delta, void* dq,
-                                void* dk, void* dv, int B, int H, int S, int head_dim, long long q_bs, long long q_ts,
+                                const void* kt, const void* dot, int Sp, const float* lse, const float* delta, const void* aug,
+                                void* dq, void* dk, void* dv, int B, int H, int S, int head_dim, long long q_bs, long long q_ts,
                                 long long k_bs, long long k_ts, long long v_bs, long long v_ts, long long do_bs,
                                 long long do_ts, long long dq_bs, long long dq_ts, long long dk_bs, long long dk_ts,
                                 long long dv_bs, long long dv_ts, const int* qid, const int* kid, const int* qmin,

@@ -38,11 +38,15 @@ def _labels(kind, B, S, dev, g):
     raise ValueError(kind)
 
 
-@pytest.mark.parametrize("impl", ["tc", "legacy"])
+@pytest.mark.parametrize("impl", ["tc", "tc-staged", "legacy"])
 @pytest.mark.parametrize("kind", ["none", "block64", "block48", "gathered", "padding"])
 @pytest.mark.parametrize("B,S,H", [(2, 512, 4), (1, 300, 2), (3, 70, 1)])
 def test_attention_fwd_bwd(kind, B, S, H, impl, monkeypatch):
+    """tc: tcgen05 kernels, backward row statistics folded into the score MMAs (default); tc-staged: the same kernels reading
+    lse / delta themselves (cross-check); legacy: the mma.sync kernels."""
     from frankenstein_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_BWD_STATS", "staged" if impl == "tc-staged" else "folded")
+    impl = "tc" if impl == "tc-staged" else impl
     monkeypatch.setattr(ops, "ATTN_BWD_IMPL", impl)
     monkeypatch.setattr(ops, "ATTN_FWD_IMPL", impl)
     g = torch.Generator().manual_seed(B * 1000 + S)
