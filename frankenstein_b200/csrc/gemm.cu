@@ -24,6 +24,7 @@
 // a 256 x 256 streamed tile needs one operand byte per 128 flops, about what the L2 fabric delivers at the bf16 peak.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "fk_b200.h"
@@ -51,6 +52,7 @@ struct GemmParams {
   int rope_len, rope_offset, rope_cols, rope_S;
   long long M;
   int N, K, nslab, ntile, nstage;
+  int cl;                    // A-resident kernel: CTAs per cluster (1, 2 or 4) that share every weight tile by TMA multicast
   int dbg;                   // diagnosis (FK_GEMM_DBG): bit 0 = the epilogue releases its accumulator without reading / storing it
 };
 
@@ -374,7 +376,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 8; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
-      mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
+      mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], static_cast<uint32_t>(p.cl));   // a stage is free once EVERY CTA of the cluster has consumed it
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
     fence_mbar_init();
@@ -385,14 +387,26 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Cluster of p.cl CTAs on p.cl different row blocks that walk the weight matrix in lock step: every CTA loads 1 / cl of
+  // each weight stage and multicasts it to all of them, so a weight byte crosses the L2 -> SM fabric once per cluster
+  // instead of once per CTA (the A-resident shapes are bound by that fabric: one weight byte per 128 flops at cl = 1).
+  const uint32_t cl = static_cast<uint32_t>(p.cl);
+  const uint32_t rank = cl > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cl_mask = static_cast<uint16_t>((1u << cl) - 1u);
+  if (cl > 1) cluster_sync_all();           // every CTA's barriers exist before a peer multicasts to them
+
   const int n_blocks = static_cast<int>((p.M + 127) / 128);
+  const int n_groups = (n_blocks + static_cast<int>(cl) - 1) / static_cast<int>(cl);     // row-block groups, one block per CTA of a cluster
+  const int n_clusters = static_cast<int>(gridDim.x / cl), cluster_id = static_cast<int>(blockIdx.x / cl);
   const int nkb = (p.K + 31) / 32;          // 32-wide k-slabs of B; A slab of k-slab j = j / 2
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     int stage = 0;
     uint32_t phase = 0, it = 0;
-    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+    const uint32_t b_part = kBStageBytes / cl, b_rows = 256u / cl;       // this CTA's share of a weight stage
+    for (int grp = cluster_id; grp < n_groups; grp += n_clusters, ++it) {
+      const int blk = grp * static_cast<int>(cl) + static_cast<int>(rank);     // (beyond M: zero-filled loads, clipped stores)
       for (int t = 0; t < p.ntile; ++t) {
         for (int j = 0; j < nkb; ++j) {
           if (t == 0 && (j & 1) == 0) {
@@ -408,7 +422,11 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           mbar_wait(&b_empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&b_full[stage], kBStageBytes);
-            tma_load_2d(Bs + stage * kBStageBytes, &tm_b, &b_full[stage], j * 32, t * 256);
+            if (cl > 1)
+              tma_load_2d_mc(Bs + stage * kBStageBytes + rank * b_part, &tm_b, &b_full[stage], j * 32,
+                             t * 256 + static_cast<int>(rank * b_rows), cl_mask);
+            else
+              tma_load_2d(Bs + stage * kBStageBytes, &tm_b, &b_full[stage], j * 32, t * 256);
           }
           __syncwarp();
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -425,7 +443,52 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // (the loop body is kept minimal: one issuing warp has to turn a 16 KB stage around in the 256 cycles its two MMAs
     //  take -- every integer division, diagnostic branch or descriptor rebuild in here showed up in the GEMM's time)
     const uint64_t adesc0 = umma_desc_sw128(as_addr), bdesc0 = umma_desc_sw64(bs_addr);
-    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+    if (p.nstage == 4 && (nkb & 3) == 0) {
+      // Fast path (K a multiple of 128, four weight stages): the ring position of every k-slab is a compile-time constant, so
+      // barrier addresses and descriptor offsets are immediates and the first / last tile of a row block (the only ones that
+      // touch the A barriers) get their own copies of the loop.  ~60 dependent instructions per 16 KB stage in the generic
+      // loop below cost more than the 256 cycles the stage's two MMAs take; this loop stays under them.
+      uint32_t ring = 0;                                   // completed passes over the 4-stage ring
+      auto run_tile = [&](auto first_c, auto last_c, uint32_t d_tmem) {
+        constexpr bool kFirst = decltype(first_c)::value, kLast = decltype(last_c)::value;
+        uint64_t adesc = adesc0;
+        for (int j4 = 0; j4 < nkb; j4 += 4, ++ring) {
+          const uint32_t ph = ring & 1;
+#pragma unroll
+          for (int st = 0; st < 4; ++st) {
+            if (kFirst && (st & 1) == 0) mbar_wait(&a_full[(j4 >> 1) + (st >> 1)], it & 1);
+            mbar_wait(&b_full[st], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t ad = adesc + static_cast<uint64_t>((st >> 1) * (kASlabBytes >> 4) + (st & 1) * 4);
+              const uint64_t bd = bdesc0 + static_cast<uint64_t>(st * (kBStageBytes >> 4));
+              umma_bf16(d_tmem, ad, bd, idesc, (j4 | st) != 0);
+              umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              if (cl > 1) umma_commit_mc(&b_empty[st], cl_mask); else umma_commit(&b_empty[st]);
+              if (kLast && (st & 1) == 1) umma_commit(&a_empty[(j4 >> 1) + (st >> 1)]);
+            }
+            __syncwarp();
+          }
+          adesc += static_cast<uint64_t>(2 * (kASlabBytes >> 4));
+        }
+      };
+      for (int grp = cluster_id; grp < n_groups; grp += n_clusters, ++it) {
+        for (int t = 0; t < p.ntile; ++t, ++tc) {
+          const uint32_t as = tc & 1;
+          mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_u + as * 256;
+          const bool ft = t == 0, lt = t == p.ntile - 1;
+          if (ft && lt) run_tile(std::true_type{}, std::true_type{}, d_tmem);
+          else if (ft) run_tile(std::true_type{}, std::false_type{}, d_tmem);
+          else if (lt) run_tile(std::false_type{}, std::true_type{}, d_tmem);
+          else run_tile(std::false_type{}, std::false_type{}, d_tmem);
+          if (elect_one()) umma_commit(&tmem_full[as]);
+          __syncwarp();
+        }
+      }
+    } else
+    for (int grp = cluster_id; grp < n_groups; grp += n_clusters, ++it) {
       for (int t = 0; t < p.ntile; ++t, ++tc) {
         const uint32_t as = tc & 1;
         mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
@@ -441,7 +504,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           if (elect_one()) {
             umma_bf16(d_tmem, adesc, bdesc, idesc, j != 0);
             umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-            umma_commit(&b_empty[stage]);
+            if (cl > 1) umma_commit_mc(&b_empty[stage], cl_mask); else umma_commit(&b_empty[stage]);
             if (last_tile && ((j & 1) == 1 || j == nkb - 1)) umma_commit(&a_empty[j >> 1]);
           }
           __syncwarp();
@@ -459,7 +522,8 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int ch = e >> 2;           // column half of the 256-column tile
     uint8_t* stg = Stg + e * kStageTileBytes;
     uint32_t tc = 0;
-    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
+      const int blk = grp * static_cast<int>(cl) + static_cast<int>(rank);
       const long long row0 = ((p.dbg & 8) ? 0ll : static_cast<long long>(blk) * 128) + q * 32;     // first row of this warp (dbg 8: every block writes rows 0..127 -> L2 only)
       const long long row = row0 + lane;
       float2 cs[16];
@@ -487,6 +551,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();           // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -850,8 +915,17 @@ FK_API int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb
   const int dev = fk_device_ordinal();
   const int G = fk_sm_count();
   if (K <= 512) {
+    // CTAs per cluster sharing each weight stage by TMA multicast (FK_GEMM_CLUSTER = 1 / 2 / 4).  Default 1: measured on
+    // B200 at M = 524288 (profiles/r02_gemm_experiments.txt), halving the weight traffic with 2-CTA clusters changes the
+    // A-resident GEMMs by < 2 % -- they are not bound by the L2 -> SM fabric but by the look-ahead of the weight ring (80 KB
+    // next to the 128 KB resident block = 1280 cycles at the full MMA rate) -- and 4-CTA clusters do not all fit at once.
+    static int cl_env = -1;
+    if (cl_env < 0) { const char* e = getenv("FK_GEMM_CLUSTER"); cl_env = e ? atoi(e) : 1; if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 1; }
+    int cl = cl_env;
+    while (cl > 1 && ((M + 127) / 128 < 2ll * cl || G % cl != 0)) cl >>= 1;
+    p.cl = cl;
     int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 128);
-    rc |= make_tmap_bf16_2d_sw64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 256);
+    rc |= make_tmap_bf16_2d_sw64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 256 / cl);
     if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
     // outputs go through the TMA store engine: 16-row x 64-column boxes, 128-byte swizzle
     CUtensorMap tc = ta, tc2 = ta;
@@ -862,30 +936,54 @@ FK_API int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb
     if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled(output) failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
     int nstage = (kGemmSmemLimit - 512 - 8 * kStageTileBytes - p.nslab * kASlabBytes) / kBStageBytes;
     if (nstage > 8) nstage = 8;
+    {
+      // FK_GEMM_STAGES = 4 selects the unrolled issue loop (K % 128 == 0) at the price of one stage of look-ahead; measured
+      // slower (0.93 against 0.83 ms for the q|k|v projection): the ring depth matters more than the issue overhead.
+      // Default: every stage that fits (5 at K = 512) with the generic loop.
+      static int st_env = -1;
+      if (st_env < 0) { const char* e = getenv("FK_GEMM_STAGES"); st_env = e ? atoi(e) : 0; }
+      if (st_env == 4 && nstage >= 4 && K % 128 == 0) nstage = 4;
+    }
     p.nstage = nstage;
     const int smem_bytes = p.nslab * kASlabBytes + nstage * kBStageBytes + 8 * kStageTileBytes + 512;
     const long long n_blocks = (M + 127) / 128;
-    const unsigned grid = static_cast<unsigned>(n_blocks < G ? n_blocks : G);
+    const long long n_groups = (n_blocks + cl - 1) / cl;
+    const long long max_clusters = G / cl;
+    const unsigned grid = static_cast<unsigned>((n_groups < max_clusters ? n_groups : max_clusters) * cl);
     static bool done[4][FK_MAX_DEVICES];
     int r2 = FK_OK;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(cl);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    cudaError_t le = cudaSuccess;
     switch (epilogue) {
       case EPI_STORE:
         if ((r2 = set_smem_attr(gemm_res_kernel<EPI_STORE>, done[0][dev], kGemmSmemLimit)) != FK_OK) return r2;
-        gemm_res_kernel<EPI_STORE><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, p);
+        le = cudaLaunchKernelEx(&cfg, gemm_res_kernel<EPI_STORE>, ta, tb, tc, tc2, p);
         break;
       case EPI_ROPE:
         if ((r2 = set_smem_attr(gemm_res_kernel<EPI_ROPE>, done[1][dev], kGemmSmemLimit)) != FK_OK) return r2;
-        gemm_res_kernel<EPI_ROPE><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, p);
+        le = cudaLaunchKernelEx(&cfg, gemm_res_kernel<EPI_ROPE>, ta, tb, tc, tc2, p);
         break;
       case EPI_SWIGLU:
         if ((r2 = set_smem_attr(gemm_res_kernel<EPI_SWIGLU>, done[2][dev], kGemmSmemLimit)) != FK_OK) return r2;
-        gemm_res_kernel<EPI_SWIGLU><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, p);
+        le = cudaLaunchKernelEx(&cfg, gemm_res_kernel<EPI_SWIGLU>, ta, tb, tc, tc2, p);
         break;
       default:
         if ((r2 = set_smem_attr(gemm_res_kernel<EPI_SWIGLU_BWD>, done[3][dev], kGemmSmemLimit)) != FK_OK) return r2;
-        gemm_res_kernel<EPI_SWIGLU_BWD><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, p);
+        le = cudaLaunchKernelEx(&cfg, gemm_res_kernel<EPI_SWIGLU_BWD>, ta, tb, tc, tc2, p);
         break;
     }
+    if (le != cudaSuccess) { fk_set_last_error(cudaGetErrorString(le), __FILE__, __LINE__); return FK_ERR_CUDA; }
   } else {
     FK_REQUIRE(epilogue == EPI_STORE, "fk_gemm_nt: fused epilogues need K <= 512 (the A-resident kernel)");
     int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 256);
