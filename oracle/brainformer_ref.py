@@ -146,9 +146,9 @@ def simple_mae_forward(sd, x, enc_cfg, dec_cfg, masked_indices, unmasked_indices
         tok = block(sd, f"encoder.transformer.h.{i}", tok, enc_cfg["n_heads"], sub, rope, rms=True, rope_last=False)
     tok = F.layer_norm(tok, (tok.shape[-1],), sd["encoder.transformer.ln_f.weight"], sd["encoder.transformer.ln_f.bias"], 1e-5)
     dec_tok = F.linear(tok, sd["decoder.emb.weight"], sd["decoder.emb.bias"])
-    dec = torch.zeros(b, t, dec_tok.shape[-1], device=dev)
+    dec = torch.zeros(b, t, dec_tok.shape[-1], device=dev, dtype=dec_tok.dtype)     # (the reference allocates x.dtype, simple_mae:371, which index_put rejects under autocast; fp32 runs are unaffected)
     dec[rows, unmasked_indices] = dec_tok
-    dec[rows, masked_indices] = sd["mask_token"]
+    dec[rows, masked_indices] = sd["mask_token"].to(dec.dtype)
     dec = dec + F.embedding(torch.cat([unmasked_indices, masked_indices], 1), sd["decoder_pos_emb.weight"])
     for i in range(n_layers(sd, "decoder.h.")):
         dec = block(sd, f"decoder.h.{i}", dec, dec_cfg["n_heads"], attn_mask[:, None], None, rms=True)

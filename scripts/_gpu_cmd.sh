@@ -1,3 +1,13 @@
 mkdir -p gpurun_out
-for c in 2 1; do echo "cluster=$c"; FK_GEMM_CLUSTER=$c timeout 300 python -m pytest tests/test_gemm_gpu.py -q -x 2>&1 | tail -2; FK_GEMM_CLUSTER=$c timeout 200 python scripts/gpu_time_gemm.py 2>&1 | head -5; done 2>&1 | tee gpurun_out/r2i_gemm_cluster.log
-echo "stages=all cluster=2"; FK_GEMM_STAGES=0 timeout 200 python scripts/gpu_time_gemm.py 2>&1 | head -4
+python bench.py > gpurun_out/r2m_bench_cfg4.json 2> gpurun_out/r2m_bench_cfg4.err; tail -2 gpurun_out/r2m_bench_cfg4.err
+for w in cfg2-encoder cfg3-mae cfg3-simple-mae cfg1-vqvae; do python bench.py --workload $w --no-cpu-baseline > gpurun_out/r2m_bench_$w.json 2> gpurun_out/r2m_bench_$w.err; tail -2 gpurun_out/r2m_bench_$w.err; done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/r2m_bench_*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        e=d.get("gpu_eager_baseline") or {}
+        print(f.split("bench_")[1], round(d["value"],1), d["unit"], round(d["ms_per_step"],2),"ms e2e",round(d["e2e"]["value"],1), "eager bf16", (e.get("bf16_autocast") or {}).get("value"), "fp32", (e.get("fp32") or {}).get("value"), "cpu", (d.get("cpu_baseline") or {}).get("value"))
+    except Exception as ex:
+        print(f, "ERR", ex)
+PY
