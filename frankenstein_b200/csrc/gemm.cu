@@ -878,7 +878,8 @@ FK_API int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(A && B && M > 0 && N > 0 && K > 0, "fk_gemm_nt: bad argument");
   FK_REQUIRE(M < (1ll << 31) - 256, "fk_gemm_nt: too many rows");
-  FK_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "fk_gemm_nt: K and the leading dimensions must be multiples of 8 (16-byte rows)");
+  // (lda < K is allowed: rows of A may overlap -- the im2col rows of a channels-last convolution are read as a view)
+  FK_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda > 0 && ldb >= K, "fk_gemm_nt: K and the leading dimensions must be multiples of 8 (16-byte rows)");
   FK_REQUIRE(N % 32 == 0, "fk_gemm_nt: N must be a multiple of 32");
   FK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "fk_gemm_nt: operands must be 16-byte aligned");
   FK_REQUIRE(epilogue >= EPI_STORE && epilogue <= EPI_SWIGLU_BWD, "fk_gemm_nt: unknown epilogue");
@@ -1032,7 +1033,8 @@ FK_API int fk_gemm_tn(const void* A, long long lda, const void* B, long long ldb
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(A && B && out && ws && M > 0 && Na > 0 && Nb > 0, "fk_gemm_tn: bad argument");
   FK_REQUIRE(M < (1ll << 31) - 64, "fk_gemm_tn: too many rows");
-  FK_REQUIRE(Na % 64 == 0 && Nb % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= Na && ldb >= Nb,
+  // (ld < N is allowed: overlapping rows, see fk_gemm_nt)
+  FK_REQUIRE(Na % 64 == 0 && Nb % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda > 0 && ldb > 0,
              "fk_gemm_tn: Na and Nb must be multiples of 64, leading dimensions multiples of 8");
   FK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0, "fk_gemm_tn: pointers must be 16-byte aligned");

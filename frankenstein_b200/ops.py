@@ -31,6 +31,15 @@ ATTN_BWD_STATS = os.environ.get("FK_ATTN_BWD_STATS", "folded")
 # ------------------------------------------------------------------------------------------------
 # LayerNorm / RMSNorm
 # ------------------------------------------------------------------------------------------------
+def _reduce_partials(dwp, dbp, w_dtype):
+    """dweight / dbias from the per-block partial sums of the norm backward: one launch for both, fixed order."""
+    nb, D = dwp.shape
+    dw = torch.empty(D, device=dwp.device, dtype=torch.float32)
+    db = torch.empty(D, device=dwp.device, dtype=torch.float32) if dbp is not None else None
+    check(lib().fk_norm_reduce_partials(ptr(dwp), ptr(dbp), nb, D, ptr(dw), ptr(db), stream()), "fk_norm_reduce_partials")
+    return dw.to(w_dtype), (db.to(w_dtype) if db is not None else None)
+
+
 class _NormFn(torch.autograd.Function):
     @staticmethod
     @on_tensor_device
@@ -75,8 +84,7 @@ class _NormFn(torch.autograd.Function):
         check(lib().fk_norm_backward(ptr(xc), _DT[xc.dtype], ptr(g), _DT[g.dtype], ptr(w), ptr(mean) if not ctx.rms else 0,
                                      ptr(rstd), ptr(dx), _DT[dx.dtype], ptr(dwp), ptr(dbp), M, D, int(ctx.rms), stream()),
               "fk_norm_backward")
-        dw = dwp.sum(0).to(ctx.w_dtype)
-        db = dbp.sum(0).to(ctx.w_dtype) if ctx.has_bias else None
+        dw, db = _reduce_partials(dwp, dbp, ctx.w_dtype)
         return dx.to(ctx.in_dtype), dw, db, None, None, None
 
 
@@ -134,8 +142,7 @@ class _AddNormFn(torch.autograd.Function):
         check(lib().fk_add_norm_backward(ptr(x_new), ptr(g_y), _DT[g_y.dtype], ptr(g_xnew), ptr(w),
                                          ptr(mean) if not ctx.rms else 0, ptr(rstd), ptr(dx), ptr(dx16), ptr(dwp), ptr(dbp),
                                          M, D, int(ctx.rms), stream()), "fk_add_norm_backward")
-        dw = dwp.sum(0).to(ctx.w_dtype)
-        db = dbp.sum(0).to(ctx.w_dtype) if ctx.has_bias else None
+        dw, db = _reduce_partials(dwp, dbp, ctx.w_dtype)
         if ctx.x_bcast:
             dx = dx.sum(0, keepdim=True)
         return dx, dx16, dw, db, None, None, None

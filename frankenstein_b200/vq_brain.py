@@ -10,19 +10,33 @@ underneath:
 * ``custom_l1_loss`` is one fused masked-sum kernel (no ``nonzero`` host sync, no dynamic shape);
 * ``calculate_perp`` is computed from the code histogram (no ``[N, K]`` one-hot).
 
-The causal conv / transposed-conv stacks are cuDNN library convolutions as in the reference
-(SURVEY.md section 8f row N1 lists them as the next kernel to write), run channels-last so that no
-permute copies or layout-conversion kernels surround them.
+* the causal conv / transposed-conv stacks run channels-last on the library's tcgen05
+  GEMMs as implicit GEMMs (``conv.py``: ``[B, T, C]`` activations, im2col rows are overlapping views of the padded
+  signal) whenever every layer's channel counts are multiples of 64; other widths, and ``FK_CONV=cudnn``, use cuDNN's
+  NHWC kernels on a 4-D view (no permute copies either way).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib
+from . import _lib, conv, gemm
 from ._lib import DTYPE_CODE, FkError, check, counters, lib, on_tensor_device, ptr, require_cuda, require_device, stream
 from .vector_quantize import VectorQuantize
+
+
+# "own" (default): the conv stacks run channels-last on the library's tcgen05 GEMMs (conv.py: im2col rows are overlapping
+# views of the padded signal); "cudnn": the same stacks as 1 x k conv2d on cuDNN's NHWC kernels (A/B comparison only).
+CONV_IMPL = os.environ.get("FK_CONV", "own")
+_CL3D = [False]      # set by _ChannelsFirstStack while its layers run on [B, T, C] activations
+
+
+def _own_conv_ok(m) -> bool:
+    return (m.padding_mode == "zeros" and conv.conv_supported(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0],
+                                                             m.dilation[0], m.groups))
 
 
 class CausalConv1d(nn.Conv1d):
@@ -33,6 +47,8 @@ class CausalConv1d(nn.Conv1d):
         self.causal_padding = self.dilation[0] * (self.kernel_size[0] - 1)
 
     def forward(self, x):
+        if _CL3D[0] and x.dim() == 3:                       # [B, T, C]: implicit GEMM on tcgen05 (conv.py)
+            return conv.causal_conv1d_cl(x, self.weight, self.bias, self.stride[0])
         if x.dim() == 4:
             # channels-last path ([B, C, 1, T] with NHWC strides, see _ChannelsFirstStack): the same convolution as a
             # 1 x k conv2d, so that cuDNN runs its NHWC kernels without a layout conversion before and after
@@ -52,6 +68,8 @@ class CausalConvTranspose1d(nn.ConvTranspose1d):
     def forward(self, x, output_size=None):
         if self.padding_mode != 'zeros':
             raise ValueError('Only `zeros` padding mode is supported for ConvTranspose1d')
+        if _CL3D[0] and x.dim() == 3:
+            return conv.causal_conv_transpose1d_cl(x, self.weight, self.bias)
         if x.dim() == 4:                                    # channels-last path (see CausalConv1d)
             y = F.conv_transpose2d(x, self.weight.unsqueeze(2), self.bias, stride=(1, self.stride[0]),
                                    padding=(0, self.padding[0]), output_padding=(0, self.output_padding[0]),
@@ -68,6 +86,8 @@ class _PointwiseConv1d(nn.Conv1d):
     """nn.Conv1d (same parameters / state-dict keys) that also takes the channels-last 4-D layout."""
 
     def forward(self, x):
+        if _CL3D[0] and x.dim() == 3:                       # 1 x 1 convolution = the plain projection of the channel axis
+            return gemm.linear(x, self.weight.squeeze(2), self.bias)
         if x.dim() == 4:
             return F.conv2d(x, self.weight.unsqueeze(2), self.bias, stride=(1, self.stride[0]),
                             padding=(0, self.padding[0]), dilation=(1, self.dilation[0]), groups=self.groups)
@@ -134,7 +154,30 @@ class _ChannelsFirstStack(nn.Module):
     [B, C, 1, T] (its NHWC strides are exactly those of a contiguous [B, T, C]), every layer is the equivalent 1 x k
     conv2d, and the result is viewed back: no permute copies and no layout-conversion kernels."""
 
+    def _own_ok(self) -> bool:
+        if getattr(self, "_own_checked", None) is None:
+            ok = True
+            for m in self.modules():
+                if isinstance(m, CausalConv1d):
+                    ok = ok and _own_conv_ok(m)
+                elif isinstance(m, CausalConvTranspose1d):
+                    ok = ok and (m.kernel_size[0] == 4 and m.stride[0] == 2 and m.dilation[0] == 1 and m.groups == 1
+                                 and m.output_padding[0] == 0 and m.in_channels % 32 == 0 and m.out_channels % 32 == 0)
+                elif isinstance(m, _PointwiseConv1d):
+                    ok = ok and (m.kernel_size[0] == 1 and m.stride[0] == 1 and m.groups == 1
+                                 and gemm.linear_supported(m.in_channels, m.out_channels))
+            self._own_checked = ok
+        return self._own_checked
+
     def forward(self, x):
+        if x.is_cuda and x.dim() == 3 and CONV_IMPL == "own" and self._own_ok():
+            # activations stay [B, T, C] bf16: every convolution is an implicit GEMM over overlapping-row views (conv.py),
+            # no permutes, no im2col copies, no cuDNN
+            _CL3D[0] = True
+            try:
+                return self.layers(x)
+            finally:
+                _CL3D[0] = False
         if x.is_cuda and x.dim() == 3 and x.is_contiguous():
             y = self.layers(x.transpose(1, 2).unsqueeze(2))          # [B, C, 1, T], channels_last strides
             return y.squeeze(2).transpose(1, 2)

@@ -116,6 +116,8 @@ int fk_norm_forward(const void* x, int x_dtype, const float* weight, const float
 /* dw_part/db_part: [fk_norm_backward_grid(), D] partial sums (caller reduces over dim 0).
  * Supported (x, g, dx): (f32,bf16,f32) (f32,f32,f32) (bf16,bf16,bf16). */
 int fk_norm_backward_grid(void);
+/* dw [D] (and db [D] when db_part != NULL) = column sums of the [nb, D] partials, one launch, fixed order. */
+int fk_norm_reduce_partials(const float* dw_part, const float* db_part, int nb, int D, float* dw, float* db, void* stream);
 int fk_norm_backward(const void* x, int x_dtype, const void* g, int g_dtype, const float* weight, const float* mean,
                      const float* rstd, void* dx, int dx_dtype, float* dw_part, float* db_part, long long M, int D,
                      int rms, void* stream);

@@ -42,9 +42,11 @@ def grads_of(model, names):
     return {n: p[n].grad.clone() for n in names}
 
 
-def soundstream_fixture(vq_mod, cosine):
-    torch.manual_seed(10 + int(cosine))
-    C, D, K, E = 32, 64, 64, 64
+def soundstream_fixture(vq_mod, cosine, C=32):
+    """C = 32: the conv widths fall outside the tcgen05 GEMMs' granularity (cuDNN path of the mirror); C = 64: every
+    convolution of the mirror runs as an implicit GEMM on the library's own kernels (conv.py)."""
+    torch.manual_seed(10 + int(cosine) + (C - 32))
+    D, K, E = 64, 64, 64
     m = quiet(vq_mod.SoundStream, C=C, D=D, codebook_size=K, n_electrodes=E, use_cosine_sim=cosine)
     cb = torch.randn(K, D) * 0.2
     if cosine:
@@ -64,7 +66,7 @@ def soundstream_fixture(vq_mod, cosine):
     names = ["encoder.layers.0.weight", "encoder.layers.2.layers.0.layers.2.bias", "encoder.layers.6.weight",
              "decoder.layers.0.weight", "decoder.layers.4.layers.0.weight", "decoder.layers.6.bias"]
     return dict(config=dict(C=C, D=D, codebook_size=K, n_electrodes=E, use_cosine_sim=cosine), state_dict=sd0, x=x,
-                loss=loss.detach(), o=o.detach(), grads=grads_of(m, names),
+                loss=loss.detach(), o=o.detach(), enc_out=e.detach(), grads=grads_of(m, names),
                 after={k: v.clone() for k, v in m.state_dict().items() if "quantizer" in k},
                 perplexity_of_arange=m.calculate_perp(torch.arange(K)[None] % 7))
 
@@ -155,6 +157,7 @@ def main():
     vq_mod, bf, sm = load_reference()
     torch.save(soundstream_fixture(vq_mod, False), os.path.join(OUT, "soundstream_euclid.pt"))
     torch.save(soundstream_fixture(vq_mod, True), os.path.join(OUT, "soundstream_cosine.pt"))
+    torch.save(soundstream_fixture(vq_mod, False, C=64), os.path.join(OUT, "soundstream_euclid_c64.pt"))
     torch.save(brainformer_fixture(bf), os.path.join(OUT, "brainformer_small.pt"))
     torch.save(simple_mae_fixture(sm), os.path.join(OUT, "simple_mae_small.pt"))
     for f in sorted(os.listdir(OUT)):
