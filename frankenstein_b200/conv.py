@@ -87,7 +87,7 @@ class _CausalConvFn(torch.autograd.Function):
             dw2 = gemm.gemm_tn(g2, A, name="conv_dw")                  # [Cout, k * Cin]
             dw = dw2.view(Cout, k, Cin).permute(0, 2, 1).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
-            db = g.sum((0, 1), dtype=torch.float32)
+            db = g2.sum(0, dtype=torch.float32)                        # (the padded copy is contiguous; its extra rows are zero)
         if ctx.needs_input_grad[0]:
             if s == 1:
                 # dx[u] = sum_j' g[u + j'] W_{k-1-j'}: im2col of the right-padded dY, taps reversed
@@ -142,7 +142,7 @@ class _CausalConvTransposeFn(torch.autograd.Function):
             d = d.view(2, Cout, 2, Cin)
             dw = torch.stack([d[0, :, 1].t(), d[1, :, 1].t(), d[0, :, 0].t(), d[1, :, 0].t()], dim=2).to(weight.dtype)    # [Cin, Cout, 4]
         if has_bias and ctx.needs_input_grad[2]:
-            db = g.sum((0, 1), dtype=torch.float32)
+            db = g2.sum(0, dtype=torch.float32).view(2, Cout).sum(0)
         if ctx.needs_input_grad[0]:
             # dx[v] = [g[2v] | g[2v+1] | g[2v+2] | g[2v+3]] . [W_0 | W_1 | W_2 | W_3]
             Ag = _rows(gbuf, M, 2, 1)

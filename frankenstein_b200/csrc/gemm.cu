@@ -113,7 +113,9 @@ __device__ __forceinline__ void to_f32(const uint32_t (&r)[32], float (&v)[32]) 
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.f / (1.f + __expf(-x)); }
+// (__fdividef: one MUFU.RCP + multiply instead of the IEEE division sequence -- the gate epilogue is bound by the length of
+//  each epilogue warp's instruction stream, not by any pipe)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // ---- coalesced epilogue I/O through a per-warp 2 KB staging tile (16 rows x 128 bytes, two passes per 32 rows) ----------
 // An accumulator row belongs to one thread (TMEM lane = row), so direct stores are 32 rows x 16 bytes per instruction:
@@ -146,12 +148,18 @@ __device__ __forceinline__ void warp_store_32x64(uint8_t* stg, int lane, const u
 }
 // Same through the TMA store engine (one bulk tensor store of the 16 x 128-byte tile per pass instead of 4 STG.128 per lane):
 // the tile layout above IS the 128-byte TMA swizzle; rows / columns outside the tensor are clipped by the hardware.
-__device__ __forceinline__ void warp_store_32x64_tma(uint8_t* stg0, int lane, const uint32_t (&w)[32], const CUtensorMap* tm,
-                                                     int col, long long row0) {
+// A warp's staging area holds `tiles` (1 or 2) such tiles used round-robin (`cnt` = passes so far): with two, the store of
+// one pass is still reading its tile while the next pass fills the other.
+__device__ __forceinline__ void warp_store_32x64_tma(uint8_t* stg0, int tiles, uint32_t& cnt, int lane, const uint32_t (&w)[32],
+                                                     const CUtensorMap* tm, int col, long long row0) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    uint8_t* stg = stg0;
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous store has read the tile
+    uint8_t* stg = stg0 + ((tiles == 2) ? (cnt & 1u) * 2048u : 0u);
+    ++cnt;
+    if (lane == 0) {                                                                   // the store that last used this tile has read it
+      if (tiles == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
     __syncwarp();
     if ((lane >> 4) == half) {
       const int r = lane & 15;
@@ -204,8 +212,9 @@ __device__ __forceinline__ void warp_load_finish_32x64(uint8_t* stg, int lane, c
 // One 128 x 256 accumulator tile of the A-resident kernels: this warp's 32 rows (TMEM lane quarter) x 128 columns (half ch).
 template <int EPI, class Release>
 __device__ __forceinline__ void res_epilogue_tile(const GemmParams& p, const CUtensorMap& tm_c, const CUtensorMap& tm_c2, uint8_t* stg,
-                                                  int lane, int ch, uint32_t taddr, int n0, long long row0, const float2 (&cs)[16],
-                                                  uint64_t* full_bar, uint32_t full_parity, Release release) {
+                                                  int stg_tiles, uint32_t& stg_cnt, int lane, int ch, uint32_t taddr, int n0,
+                                                  long long row0, const float2 (&cs)[16], uint64_t* full_bar, uint32_t full_parity,
+                                                  Release release) {
     const long long row = row0 + lane;
     (void)row;
     if (p.dbg & 1) {
@@ -252,7 +261,7 @@ __device__ __forceinline__ void res_epilogue_tile(const GemmParams& p, const CUt
         }
         if (col < p.N) {
           if (p.dbg & 4) warp_store_32x64(stg, lane, w, p.C + col, p.ldc, row0, p.M, p.dbg);     // diagnosis: LSU stores (N % 64 == 0)
-          else warp_store_32x64_tma(stg, lane, w, &tm_c, col, row0);
+          else warp_store_32x64_tma(stg, stg_tiles, stg_cnt, lane, w, &tm_c, col, row0);
         }
       }
     } else if (EPI == EPI_SWIGLU) {
@@ -285,15 +294,15 @@ __device__ __forceinline__ void res_epilogue_tile(const GemmParams& p, const CUt
       }
       const int ca = n0 + ch * 64;                            // column of the w1 part inside h13
       if (ca < p.N) {
-        warp_store_32x64_tma(stg, lane, wa, &tm_c, ca, row0);
-        warp_store_32x64_tma(stg, lane, wb, &tm_c, ca + 128, row0);
+        warp_store_32x64_tma(stg, stg_tiles, stg_cnt, lane, wa, &tm_c, ca, row0);
+        warp_store_32x64_tma(stg, stg_tiles, stg_cnt, lane, wb, &tm_c, ca + 128, row0);
         // the saved h13 is bf16: gate from the ROUNDED values, so that backward (which reads h13) sees the same function
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float a0 = bf16_lo(wa[i]), a1 = bf16_hi(wa[i]), b0 = bf16_lo(wb[i]), b1 = bf16_hi(wb[i]);
           wa[i] = pack_bf16(a0 * sigmoidf_fast(a0) * b0, a1 * sigmoidf_fast(a1) * b1);
         }
-        warp_store_32x64_tma(stg, lane, wa, &tm_c2, (n0 >> 1) + ch * 64, row0);
+        warp_store_32x64_tma(stg, stg_tiles, stg_cnt, lane, wa, &tm_c2, (n0 >> 1) + ch * 64, row0);
       }
     } else {   // EPI_SWIGLU_BWD: accumulator = d gated [M, N]; this warp: hidden block n0/128 + ch (128 units)
       const long long o0 = 2ll * (n0 + ch * 128);             // column of h1 of the block inside the interleaved h13 / dh13
@@ -340,8 +349,8 @@ __device__ __forceinline__ void res_epilogue_tile(const GemmParams& p, const CUt
           warp_load_issue_32x64(p.aux + o0 + 64 + 128, p.ld_aux, row0, p.M, lane, g3);
         }
         if (ok) {
-          warp_store_32x64_tma(stg, lane, w1, &tm_c2, static_cast<int>(o0) + dc * 64, row0);
-          warp_store_32x64_tma(stg, lane, w3, &tm_c2, static_cast<int>(o0) + dc * 64 + 128, row0);
+          warp_store_32x64_tma(stg, stg_tiles, stg_cnt, lane, w1, &tm_c2, static_cast<int>(o0) + dc * 64, row0);
+          warp_store_32x64_tma(stg, stg_tiles, stg_cnt, lane, w3, &tm_c2, static_cast<int>(o0) + dc * 64 + 128, row0);
         }
       }
     }
@@ -521,7 +530,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int q = warp & 3;          // TMEM lane quarter this warp may read
     const int ch = e >> 2;           // column half of the 256-column tile
     uint8_t* stg = Stg + e * kStageTileBytes;
-    uint32_t tc = 0;
+    uint32_t tc = 0, stg_cnt = 0;
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int blk = grp * static_cast<int>(cl) + static_cast<int>(rank);
       const long long row0 = ((p.dbg & 8) ? 0ll : static_cast<long long>(blk) * 128) + q * 32;     // first row of this warp (dbg 8: every block writes rows 0..127 -> L2 only)
@@ -543,7 +552,7 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[as]);
         };
-        res_epilogue_tile<EPI>(p, tm_c, tm_c2, stg, lane, ch, taddr, n0, row0, cs, &tmem_full[as], (tc >> 1) & 1, release);
+        res_epilogue_tile<EPI>(p, tm_c, tm_c2, stg, 1, stg_cnt, lane, ch, taddr, n0, row0, cs, &tmem_full[as], (tc >> 1) & 1, release);
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all bulk stores of this warp have completed
@@ -553,6 +562,161 @@ gemm_res_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   if (cl > 1) cluster_sync_all();           // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ================================================================================================
+// A-resident kernel on CTA PAIRS (cta_group::2): two SMs of one TPC own two adjacent 128-row blocks (both resident) and
+// work on ONE 256 x 256 tile at a time.  Each CTA streams only HALF of every weight stage (128 of the 256 weight rows,
+// 8 KB instead of 16 KB) -- the tensor cores of both SMs read both halves -- so the same 80 KB next to the resident block
+// hold 10 stages instead of 5: twice the look-ahead, which is what bounds the single-CTA kernel (profiles/r02_gemm_experiments.txt).
+// The leader CTA (cluster rank 0) issues every MMA; both CTAs run their own TMA producer (completion bytes go to the
+// LEADER's full barriers) and their own epilogue on their own TMEM (rows 0-127 / 128-255 of the tile).
+// ================================================================================================
+constexpr int kB2StageBytes = 128 * 64;    // this CTA's half of a weight stage: 128 rows x 32 bf16
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_res2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_c2, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* As = smem;                                        // nslab x 16 KB
+  uint8_t* Bs = As + p.nslab * kASlabBytes;                  // nstage x 8 KB
+  uint8_t* Stg = Bs + p.nstage * kB2StageBytes;              // 8 warps x 2 x 2 KB epilogue staging tiles (double buffered)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Stg + 16 * kStageTileBytes);
+  uint64_t* a_full = bars;            // [8]   (waited on in the leader only)
+  uint64_t* a_empty = bars + 8;       // [8]
+  uint64_t* b_full = bars + 16;       // [16]  (leader only)
+  uint64_t* b_empty = bars + 32;      // [16]
+  uint64_t* tmem_full = bars + 48;    // [2]
+  uint64_t* tmem_empty = bars + 50;   // [2]   (leader only: 8 epilogue warps of each CTA arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 52);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_c2); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 16; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // both CTAs' barriers and TMEM exist before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_blocks = static_cast<int>((p.M + 127) / 128);
+  const int n_groups = (n_blocks + 1) / 2;
+  const int n_pairs = static_cast<int>(gridDim.x / 2), pair_id = static_cast<int>(blockIdx.x / 2);
+  const int nkb = (p.K + 31) / 32;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    int stage = 0;
+    uint32_t phase = 0, it = 0;
+    for (int grp = pair_id; grp < n_groups; grp += n_pairs, ++it) {
+      const int blk = grp * 2 + static_cast<int>(rank);
+      for (int t = 0; t < p.ntile; ++t) {
+        for (int j = 0; j < nkb; ++j) {
+          if (t == 0 && (j & 1) == 0) {
+            const int ks = j >> 1;
+            mbar_wait(&a_empty[ks], (it & 1) ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&a_full[ks], 2 * kASlabBytes);          // this CTA's slab + the peer's
+              tma_load_2d_2sm(As + ks * kASlabBytes, &tm_a, mapa_shared(smem_u32(&a_full[ks]), 0), ks * 64, blk * 128);
+            }
+            __syncwarp();
+          }
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&b_full[stage], 2 * kB2StageBytes);
+            tma_load_2d_2sm(Bs + stage * kB2StageBytes, &tm_b, mapa_shared(smem_u32(&b_full[stage]), 0), j * 32,
+                            t * 256 + static_cast<int>(rank) * 128);
+          }
+          __syncwarp();
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ================================ MMA issuer (leader CTA) ================================
+    constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t adesc0 = umma_desc_sw128(smem_u32(As)), bdesc0 = umma_desc_sw64(smem_u32(Bs));
+    int stage = 0;
+    uint32_t phase = 0, it = 0, tc = 0;
+    for (int grp = pair_id; grp < n_groups; grp += n_pairs, ++it) {
+      for (int t = 0; t < p.ntile; ++t, ++tc) {
+        const uint32_t as = tc & 1;
+        mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + as * 256;
+        const bool first_tile = t == 0, last_tile = t == p.ntile - 1;
+        uint64_t adesc = adesc0;
+        for (int j = 0; j < nkb; ++j) {
+          if (first_tile && (j & 1) == 0) mbar_wait(&a_full[j >> 1], it & 1);
+          mbar_wait(&b_full[stage], phase);
+          tc_fence_after();
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (kB2StageBytes >> 4));
+          if (elect_one()) {
+            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, j != 0);
+            umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            umma_commit_2sm(&b_empty[stage], 3);
+            if (last_tile && ((j & 1) == 1 || j == nkb - 1)) umma_commit_2sm(&a_empty[j >> 1], 3);
+          }
+          __syncwarp();
+          adesc += (j & 1) ? static_cast<uint64_t>((kASlabBytes >> 4) - 4) : 4ull;
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit_2sm(&tmem_full[as], 3);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs, own TMEM) ================================
+    const int e = warp - 4;
+    const int q = warp & 3;
+    const int ch = e >> 2;
+    uint8_t* stg = Stg + e * 2 * kStageTileBytes;
+    uint32_t tc = 0, stg_cnt = 0;
+    for (int grp = pair_id; grp < n_groups; grp += n_pairs) {
+      const int blk = grp * 2 + static_cast<int>(rank);
+      const long long row0 = static_cast<long long>(blk) * 128 + q * 32;
+      const long long row = row0 + lane;
+      float2 cs[16];
+      if (EPI == EPI_ROPE) {
+        int ps = 0;
+        if (row < p.M) ps = p.rope_pos ? p.rope_pos[row] : static_cast<int>(row % p.rope_S) + p.rope_offset;
+        ps = min(max(ps, 0), p.rope_len - 1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cs[i] = __ldg(p.rope_table + static_cast<long long>(ps) * 16 + i);
+      }
+      for (int t = 0; t < p.ntile; ++t, ++tc) {
+        const uint32_t as = tc & 1;
+        const int n0 = t * 256;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+        auto release = [&]() {           // this warp has read its part of the accumulator stage: tell the leader's issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(&tmem_empty[as]);
+            else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+          }
+        };
+        res_epilogue_tile<EPI>(p, tm_c, tm_c2, stg, 2, stg_cnt, lane, ch, taddr, n0, row0, cs, &tmem_full[as], (tc >> 1) & 1, release);
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
 }
 
 // ================================================================================================
@@ -925,6 +1089,61 @@ FK_API int fk_gemm_nt(const void* A, long long lda, const void* B, long long ldb
     int cl = cl_env;
     while (cl > 1 && ((M + 127) / 128 < 2ll * cl || G % cl != 0)) cl >>= 1;
     p.cl = cl;
+    // CTA pairs (cta_group::2, gemm_res2_kernel; default): FK_GEMM_PAIR = 0 selects the single-CTA kernel below (also used
+    // when the problem has fewer than 4 row blocks or the device an odd number of SMs)
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("FK_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
+    if (pair_env && (M + 127) / 128 >= 4 && G % 2 == 0) {
+      int rc2 = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 128);
+      rc2 |= make_tmap_bf16_2d_sw64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 128);
+      CUtensorMap tc = ta, tc2 = ta;
+      if (C != nullptr) rc2 |= make_tmap_bf16_2d(&tc, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldc), 16);
+      if (C2 != nullptr)
+        rc2 |= make_tmap_bf16_2d(&tc2, C2, static_cast<uint64_t>(M), static_cast<uint64_t>(epilogue == EPI_SWIGLU ? N / 2 : 2 * N),
+                                 static_cast<uint64_t>(ldc2), 16);
+      if (rc2 != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }
+      int nstage = (kGemmSmemLimit - 512 - 16 * kStageTileBytes - p.nslab * kASlabBytes) / kB2StageBytes;
+      if (nstage > 16) nstage = 16;
+      p.nstage = nstage;
+      const int smem_bytes = p.nslab * kASlabBytes + nstage * kB2StageBytes + 16 * kStageTileBytes + 512;
+      const long long n_groups = ((M + 127) / 128 + 1) / 2;
+      const long long max_pairs = G / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>((n_groups < max_pairs ? n_groups : max_pairs) * 2), 1, 1);
+      cfg.blockDim = dim3(kGemmThreads, 1, 1);
+      cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      static bool done2[4][FK_MAX_DEVICES];
+      int r2 = FK_OK;
+      cudaError_t le = cudaSuccess;
+      switch (epilogue) {
+        case EPI_STORE:
+          if ((r2 = set_smem_attr(gemm_res2_kernel<EPI_STORE>, done2[0][dev], kGemmSmemLimit)) != FK_OK) return r2;
+          le = cudaLaunchKernelEx(&cfg, gemm_res2_kernel<EPI_STORE>, ta, tb, tc, tc2, p);
+          break;
+        case EPI_ROPE:
+          if ((r2 = set_smem_attr(gemm_res2_kernel<EPI_ROPE>, done2[1][dev], kGemmSmemLimit)) != FK_OK) return r2;
+          le = cudaLaunchKernelEx(&cfg, gemm_res2_kernel<EPI_ROPE>, ta, tb, tc, tc2, p);
+          break;
+        case EPI_SWIGLU:
+          if ((r2 = set_smem_attr(gemm_res2_kernel<EPI_SWIGLU>, done2[2][dev], kGemmSmemLimit)) != FK_OK) return r2;
+          le = cudaLaunchKernelEx(&cfg, gemm_res2_kernel<EPI_SWIGLU>, ta, tb, tc, tc2, p);
+          break;
+        default:
+          if ((r2 = set_smem_attr(gemm_res2_kernel<EPI_SWIGLU_BWD>, done2[3][dev], kGemmSmemLimit)) != FK_OK) return r2;
+          le = cudaLaunchKernelEx(&cfg, gemm_res2_kernel<EPI_SWIGLU_BWD>, ta, tb, tc, tc2, p);
+          break;
+      }
+      if (le != cudaSuccess) { fk_set_last_error(cudaGetErrorString(le), __FILE__, __LINE__); return FK_ERR_CUDA; }
+      FK_CHECK_LAUNCH();
+      fk_count_launch(1);
+      return FK_OK;
+    }
     int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 128);
     rc |= make_tmap_bf16_2d_sw64(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 256 / cl);
     if (rc != FK_OK) { fk_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return FK_ERR_DRIVER; }

@@ -312,26 +312,28 @@ FK_API int fk_norm_forward(const void* x, int x_dtype, const float* weight, cons
 FK_API int fk_norm_backward_grid(void) { return 148 * 4; }
 
 // dweight / dbias = column sums of the per-block partials [nb, D] of fk_norm_backward / fk_add_norm_backward: both in ONE
-// launch, rows added in a fixed order (deterministic).  Block = 32 columns x 8 row groups.
+// launch, rows added in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 norm_partials_reduce_kernel(const float* __restrict__ dw_part, const float* __restrict__ db_part, int nb, int D,
                             float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float red[2][8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rg = threadIdx.x >> 5;
+  // block = 8 columns x 32 row groups (D / 8 blocks: enough CTAs in flight for a 2.4 MB read)
+  __shared__ float red[2][32][9];
+  const int cl = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   float a = 0.f, b = 0.f;
   if (c < D) {
-    for (int r = rg; r < nb; r += 8) {
+    for (int r = rg; r < nb; r += 32) {
       a += dw_part[static_cast<long long>(r) * D + c];
       if (db_part != nullptr) b += db_part[static_cast<long long>(r) * D + c];
     }
   }
-  red[0][rg][threadIdx.x & 31] = a;
-  red[1][rg][threadIdx.x & 31] = b;
+  red[0][rg][cl] = a;
+  red[1][rg][cl] = b;
   __syncthreads();
   if (rg == 0 && c < D) {
     float sa = 0.f, sb = 0.f;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) { sa += red[0][g][threadIdx.x]; sb += red[1][g][threadIdx.x]; }
+#pragma unroll 8
+    for (int g = 0; g < 32; ++g) { sa += red[0][g][cl]; sb += red[1][g][cl]; }
     dw[c] = sa;
     if (db_part != nullptr) db[c] = sb;
   }
@@ -340,7 +342,7 @@ norm_partials_reduce_kernel(const float* __restrict__ dw_part, const float* __re
 FK_API int fk_norm_reduce_partials(const float* dw_part, const float* db_part, int nb, int D, float* dw, float* db, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FK_REQUIRE(dw_part && dw && nb > 0 && D > 0 && (db_part == nullptr || db != nullptr), "fk_norm_reduce_partials: bad argument");
-  norm_partials_reduce_kernel<<<static_cast<unsigned>((D + 31) / 32), 256, 0, stream>>>(dw_part, db_part, nb, D, dw, db);
+  norm_partials_reduce_kernel<<<static_cast<unsigned>((D + 7) / 8), 256, 0, stream>>>(dw_part, db_part, nb, D, dw, db);
   FK_CHECK_LAUNCH();
   fk_count_launch();
   return FK_OK;
