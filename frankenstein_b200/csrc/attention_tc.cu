@@ -36,6 +36,13 @@ constexpr int kNG = 3;            // score stages in TMEM = tiles in flight = co
 constexpr int kSub = kCols / 16;              // 16-column sub-chunks per tile
 constexpr int kTcThreads = 128 + 128 * kNG;
 constexpr int kAccCol = 128 * kNG;
+// Resident operands of the score MMAs in TMEM (TS mode: a tcgen05.mma with its A operand in TMEM costs N/2 = 32 cycles at
+// N = 64, against the 48-cycle floor of the shared-memory form): columns 448.. hold the two resident tiles as packed bf16
+// pairs (16 columns each), the two constant ones tiles of the folded statistics (8 each) and, for the dQ kernel, the
+// resident queries' statistics rows (8).
+constexpr int kResCol = kAccCol + 64;         // 448: resident A (K / Q), +16: resident B (V / dO)
+constexpr int kOnesCol = kResCol + 32;        // 480: ones(cols 0-2), +8: ones(cols 3-5)
+constexpr int kAugCol = kOnesCol + 16;        // 496: DQ statistics rows
 constexpr int kMaxTiles = 2048;   // streamed tiles per sequence (S <= 131072); entries carry a flag in bit 15
 constexpr int MODE_DKV = 0, MODE_DQ = 1;
 
@@ -190,9 +197,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   uint64_t* acc_full = p_ready + kNG;      // [1]
   uint64_t* dp_full = acc_full + 1;        // [kNG]  fold: dP of stage g written (sdp_full then announces S alone, so the
                                            //        exponentials of a tile start while its dP MMAs still run)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dp_full + kNG);
-  int* n_tiles_slot = reinterpret_cast<int*>(dp_full + kNG) + 1;   // [2]
-  int* item_slot = reinterpret_cast<int*>(dp_full + kNG) + 3;      // [2]: item ids handed to this CTA, double buffered
+  uint64_t* res_tmem = dp_full + kNG;      // [1]    warpgroup 0 has copied the item's resident tiles into TMEM (4 warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_tmem + 1);
+  int* n_tiles_slot = reinterpret_cast<int*>(res_tmem + 1) + 1;   // [2]
+  int* item_slot = reinterpret_cast<int*>(res_tmem + 1) + 3;      // [2]: item ids handed to this CTA, double buffered
   uint16_t* tile_lists = reinterpret_cast<uint16_t*>(smem + TcSmem::tiles);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,6 +228,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       mbar_init(&dp_full[i], 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(res_tmem, 4);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -243,6 +252,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (fold && MODE == MODE_DKV && warp >= 4 && warp < 8) {
+    // constant A operands of the statistics K step, one row per thread: 16 bf16 = 8 packed columns
+    const uint32_t t0 = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kOnesCol;
+    const uint32_t os[8] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u};      // ones in elements 0-2
+    const uint32_t od[8] = {0u, 0x3F800000u, 0x3F803F80u, 0u, 0u, 0u, 0u, 0u};      // ones in elements 3-5
+    tmem_st8(t0, os);
+    tmem_st8(t0 + 8, od);
+    tmem_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
 
   // ---- persistent loop over work items (row tile, head, batch): barriers, TMEM and the smem rings live across items,
   //      which removes the 1-1.6 us launch gap between consecutive CTAs of an SM and the per-CTA setup.  All barrier
@@ -388,8 +409,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       const uint64_t dA = umma_desc_sw64(smem_u32(smem + TcSmem::resA + (item_n & 1) * 16384)),
                      dB = umma_desc_sw64(smem_u32(smem + TcSmem::resB + (item_n & 1) * 16384));
       const uint32_t stream = smem_u32(smem + TcSmem::stream);
-      mbar_wait(&res_full[item_n & 1], (item_n >> 1) & 1);
+      (void)dA; (void)dB;
+      mbar_wait(res_tmem, item_n & 1);                // the resident tiles of this item sit in TMEM (copied by warpgroup 0)
       tc_fence_after();
+      const uint32_t tA = tmem_u + kResCol, tB = tmem_u + kResCol + 16;
       long long w_sf = 0, w_free = 0;
       for (int js = 0; js < T_u; ++js) {
         const int gt = base + js;                    // tile counter across items
@@ -403,14 +426,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         //                           DQ   A = the resident queries' statistics, B = constant ones tile (keys)
         uint64_t fA_s = 0, fA_d = 0, fB_s = 0, fB_d = 0;
         if constexpr (fold) {
-          fA_s = umma_desc_sw32(smem_u32(smem + TcSmem::ones));
-          fA_d = umma_desc_sw32(smem_u32(smem + TcSmem::ones + 4096));
+          // B operands of the statistics K step (its A operands are in TMEM): DKV the tile's statistics rows, DQ the ones tiles
           fB_s = fB_d = umma_desc_sw32(stream + stage * 16384 + 8192);
           if (MODE == MODE_DQ) {
-            fB_s = fA_s; fB_d = fA_d;
-            fA_s = fA_d = umma_desc_sw32(smem_u32(smem + TcSmem::aug_res + (item_n & 1) * 4096));
+            fB_s = umma_desc_sw32(smem_u32(smem + TcSmem::ones));
+            fB_d = umma_desc_sw32(smem_u32(smem + TcSmem::ones + 4096));
           }
-          asm volatile("" : "+l"(fA_s), "+l"(fA_d), "+l"(fB_s), "+l"(fB_d));
+          (void)fA_s; (void)fA_d;
+          asm volatile("" : "+l"(fB_s), "+l"(fB_d));
         }
         {
           // pin the values here: without this the compiler sinks the whole address arithmetic below the waits again
@@ -422,16 +445,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         tc_fence_after();
         if (elect_one()) {
           // a K step of 16 bf16 = 32 bytes = +2 in the descriptor's (address >> 4) field
-          umma_bf16(d_s, dA, dS, idesc_score, 0u);
-          umma_bf16(d_s, dA + 2, dS + 2, idesc_score, 1u);
+          // TS mode: A = the resident tile in TMEM (K step of 16 elements = 8 packed columns)
+          umma_bf16_ts(d_s, tA, dS, idesc_score, 0u);
+          umma_bf16_ts(d_s, tA + 8, dS + 2, idesc_score, 1u);
           if (fold) {
-            umma_bf16(d_s, fA_s, fB_s, idesc_score, 1u);
+            umma_bf16_ts(d_s, MODE == MODE_DKV ? tmem_u + kOnesCol : tmem_u + kAugCol, fB_s, idesc_score, 1u);
             umma_commit(bar_full);                         // S' complete: the warpgroup starts on the exponentials
           }
-          umma_bf16(d_dp, dB, dD, idesc_score, 0u);
-          umma_bf16(d_dp, dB + 2, dD + 2, idesc_score, 1u);
+          umma_bf16_ts(d_dp, tB, dD, idesc_score, 0u);
+          umma_bf16_ts(d_dp, tB + 8, dD + 2, idesc_score, 1u);
           if (fold) {
-            umma_bf16(d_dp, fA_d, fB_d, idesc_score, 1u);
+            umma_bf16_ts(d_dp, MODE == MODE_DKV ? tmem_u + kOnesCol + 8 : tmem_u + kAugCol, fB_d, idesc_score, 1u);
             umma_commit(&dp_full[g]);
           } else {
             umma_commit(bar_full);
@@ -512,6 +536,38 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
                              : 0;
     float my_lse = INFINITY, my_delta = 0.f;     // DQ: per-row statistics
     if (MODE == MODE_DQ && row_ok && !fold) { my_lse = lse_g[row]; my_delta = delta_g[row]; }
+    if (g == 0) {
+      // resident tiles of this item: shared memory (TMA, 64-byte rows, SWIZZLE_64B) -> this thread's TMEM lane as packed
+      // bf16 pairs, the A operand layout of a TS-mode MMA.  (Every MMA of the previous item has retired: the item loop
+      // ends with a CTA-wide barrier behind acc_full.)
+      mbar_wait(&res_full[item_n & 1], (item_n >> 1) & 1);
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+      const int sw = (r >> 1) & 3;
+#pragma unroll
+      for (int t2 = 0; t2 < 2; ++t2) {
+        const uint8_t* rowp = smem + (t2 ? TcSmem::resB : TcSmem::resA) + (item_n & 1) * 16384 + r * 64;
+        uint32_t v[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
+          v[4 * c] = w.x; v[4 * c + 1] = w.y; v[4 * c + 2] = w.z; v[4 * c + 3] = w.w;
+        }
+        tmem_st16(lane_addr + kResCol + t2 * 16, v);
+      }
+      if (fold && MODE == MODE_DQ) {
+        // statistics rows of the resident queries (32-byte rows, SWIZZLE_32B: the halves swap when bit 2 of r is set)
+        const uint8_t* rowp = smem + TcSmem::aug_res + (item_n & 1) * 4096 + r * 32;
+        const int s1 = (r >> 2) & 1;
+        const uint4 w0 = *reinterpret_cast<const uint4*>(rowp + ((0 ^ s1) << 4));
+        const uint4 w1 = *reinterpret_cast<const uint4*>(rowp + ((1 ^ s1) << 4));
+        const uint32_t a8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        tmem_st8(lane_addr + kAugCol, a8);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(res_tmem);
+    }
 
     // column statistics of a streamed tile, fetched one own-tile ahead
     float pre_f = 0.f;

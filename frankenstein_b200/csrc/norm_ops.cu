@@ -103,47 +103,96 @@ norm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const fl
 // dw / db partial sums per CTA -> [gridDim.x, D]; the caller sums the partials.
 // Persistent CTAs: each warp strides over rows and keeps its dw/db partials in registers.
 // ------------------------------------------------------------------------------------------------
+// Software pipelined: a warp issues the loads of its NEXT row (x, dy and the residual-path gradient) before it reduces
+// and stores the current one, so every warp keeps a full row (5 KB at D = 512) in flight all the time -- with the loads
+// of one row at a time and the residual gradient fetched after the reduction (two dependent DRAM round trips per row)
+// the kernel sat at half of the HBM peak.  One CTA of kNormBwdWarps warps per SM, up to 168 registers per thread.
+constexpr int kNormBwdWarps = 12;
+#ifndef FK_NORM_BWD_AHEAD
+#define FK_NORM_BWD_AHEAD 2
+#endif
+constexpr int kNormBwdAhead = FK_NORM_BWD_AHEAD;     // rows per warp in flight (1 in registers, the rest on their way into L2)
+
 template <typename TIn, typename TG, typename TDx, int MAXV>
-__global__ void __launch_bounds__(kNormWarps * 32)
+__global__ void __launch_bounds__(kNormBwdWarps * 32, 1)
 norm_bwd_kernel(const TIn* __restrict__ x, const TG* __restrict__ g, const float* __restrict__ w, const float* __restrict__ mean_in,
                 const float* __restrict__ rstd_in, TDx* __restrict__ dx, float* __restrict__ dw_part, float* __restrict__ db_part,
                 long long M, int D, int rms, const float* __restrict__ g_res = nullptr, __nv_bfloat16* __restrict__ dx_bf16 = nullptr) {
   // g_res: gradient that reaches x through the residual path (added to dx); dx_bf16: second copy of dx for the
   // bf16 branch of the fused residual add (x_new = x + delta  =>  d delta = d x = dx)
-  extern __shared__ float sm[];        // [kNormWarps][2][D]
+  extern __shared__ float sm[];        // [D] weight, then [kNormBwdWarps][D] for the final reduction
+  float* w_s = sm;
+  float* red = sm + D;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float dw[MAXV][4], db[MAXV][4], wv[MAXV][4];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) w_s[d] = w[d];
+  __syncthreads();
+  float dw[MAXV][4], db[MAXV][4];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int d = (i * 32 + lane) * 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { dw[i][j] = 0.f; db[i][j] = 0.f; wv[i][j] = 0.f; }
-    if (d < D) Vec4<float>::load(w + d, wv[i]);
+    for (int j = 0; j < 4; ++j) { dw[i][j] = 0.f; db[i][j] = 0.f; }
   }
-  for (long long row = static_cast<long long>(blockIdx.x) * kNormWarps + warp; row < M;
-       row += static_cast<long long>(gridDim.x) * kNormWarps) {
-    const float mean = rms ? 0.f : mean_in[row], rstd = rstd_in[row];
-    float xh[MAXV][4], gw[MAXV][4];
+  const long long stride = static_cast<long long>(gridDim.x) * kNormBwdWarps;
+  long long row = static_cast<long long>(blockIdx.x) * kNormBwdWarps + warp;
+  const bool has_res = g_res != nullptr;
+  float nx[MAXV][4], ng[MAXV][4], nr[MAXV][4], nmean = 0.f, nrstd = 0.f;
+  auto fetch = [&](long long r) {
+    nmean = rms ? 0.f : mean_in[r];
+    nrstd = rstd_in[r];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int d = (i * 32 + lane) * 4;
+      if (d < D) {
+        Vec4<TIn>::load(x + r * D + d, nx[i]);
+        Vec4<TG>::load(g + r * D + d, ng[i]);
+        if (has_res) Vec4<float>::load(g_res + r * D + d, nr[i]);
+      }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { nx[i][j] = 0.f; ng[i][j] = 0.f; nr[i][j] = 0.f; }
+  }
+  // rows further ahead are pulled into L2 by bulk prefetches (one lane, no registers), so that the register loads of the
+  // next row find them there: kNormBwdAhead rows per warp on their way from DRAM at any time
+  const bool pf_ok = (D * sizeof(TIn)) % 16 == 0 && (D * sizeof(TG)) % 16 == 0;
+  auto prefetch_l2 = [&](long long r) {
+    if (!pf_ok || r >= M || lane != 0) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + r * D), "r"(static_cast<uint32_t>(D * sizeof(TIn))) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g + r * D), "r"(static_cast<uint32_t>(D * sizeof(TG))) : "memory");
+    if (has_res)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g_res + r * D), "r"(static_cast<uint32_t>(D * sizeof(float))) : "memory");
+  };
+  if (row < M) fetch(row);
+#pragma unroll
+  for (int a = 1; a < kNormBwdAhead; ++a) prefetch_l2(row + a * stride);
+  for (; row < M; row += stride) {
+    prefetch_l2(row + kNormBwdAhead * stride);
+    float xh[MAXV][4], gv[MAXV][4], gr[MAXV][4];
+    const float mean = nmean, rstd = nrstd;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xh[i][j] = nx[i][j]; gv[i][j] = ng[i][j]; gr[i][j] = nr[i][j]; }
+    }
+    if (row + stride < M) fetch(row + stride);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int d = (i * 32 + lane) * 4;
       if (d < D) {
-        float xv[4], gv[4];
-        Vec4<TIn>::load(x + row * D + d, xv);
-        Vec4<TG>::load(g + row * D + d, gv);
+        float wv[4];
+        Vec4<float>::load(w_s + d, wv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          gw[i][j] = gv[j] * wv[i][j];
-          dw[i][j] += gv[j] * xh[i][j];
-          db[i][j] += gv[j];
-          s1 += gw[i][j];
-          s2 += gw[i][j] * xh[i][j];
+          xh[i][j] = (xh[i][j] - mean) * rstd;
+          dw[i][j] += gv[i][j] * xh[i][j];
+          db[i][j] += gv[i][j];
+          gv[i][j] *= wv[j];                       // gw
+          s1 += gv[i][j];
+          s2 += gv[i][j] * xh[i][j];
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { xh[i][j] = 0.f; gw[i][j] = 0.f; }
       }
     }
     s1 = rms ? 0.f : warp_sum(s1) / D;
@@ -154,37 +203,33 @@ norm_bwd_kernel(const TIn* __restrict__ x, const TG* __restrict__ g, const float
       if (d < D) {
         float o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = rstd * (gw[i][j] - s1 - xh[i][j] * s2);
-        if (g_res != nullptr) {
-          float gr[4];
-          Vec4<float>::load(g_res + row * D + d, gr);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] += gr[j];
+        for (int j = 0; j < 4; ++j) {
+          o[j] = rstd * (gv[i][j] - s1 - xh[i][j] * s2);
+          if (has_res) o[j] += gr[i][j];
         }
         Vec4<TDx>::store(dx + row * D + d, o);
         if (dx_bf16 != nullptr) Vec4<__nv_bfloat16>::store(dx_bf16 + row * D + d, o);
       }
     }
   }
-  // CTA reduction of the parameter-gradient partials
+  // CTA reduction of the parameter-gradient partials (dweight, then dbias, through one [warps][D] buffer)
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int d = (i * 32 + lane) * 4;
-    if (d < D) {
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1 && db_part == nullptr) break;
+    __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        sm[(warp * 2 + 0) * D + d + j] = dw[i][j];
-        sm[(warp * 2 + 1) * D + d + j] = db[i][j];
-      }
+    for (int i = 0; i < MAXV; ++i) {
+      const int d = (i * 32 + lane) * 4;
+      if (d < D) Vec4<float>::store(red + warp * D + d, pass == 0 ? dw[i] : db[i]);
     }
-  }
-  __syncthreads();
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float a = 0.f, b = 0.f;
+    __syncthreads();
+    float* out = pass == 0 ? dw_part : db_part;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float a = 0.f;
 #pragma unroll
-    for (int wi = 0; wi < kNormWarps; ++wi) { a += sm[(wi * 2 + 0) * D + d]; b += sm[(wi * 2 + 1) * D + d]; }
-    dw_part[static_cast<long long>(blockIdx.x) * D + d] = a;
-    if (db_part) db_part[static_cast<long long>(blockIdx.x) * D + d] = b;
+      for (int wi = 0; wi < kNormBwdWarps; ++wi) a += red[wi * D + d];
+      out[static_cast<long long>(blockIdx.x) * D + d] = a;
+    }
   }
 }
 
@@ -279,10 +324,10 @@ static int launch_norm_bwd(const void* x, const void* g, const float* w, const f
   const TIn* xi = static_cast<const TIn*>(x);
   const TG* gi = static_cast<const TG*>(g);
   TDx* dxo = static_cast<TDx*>(dx);
-  const size_t smem = static_cast<size_t>(kNormWarps) * 2 * D * sizeof(float);
-  if (D <= 128) norm_bwd_kernel<TIn, TG, TDx, 1><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
-  else if (D <= 256) norm_bwd_kernel<TIn, TG, TDx, 2><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
-  else if (D <= 512) norm_bwd_kernel<TIn, TG, TDx, 4><<<grid, kNormWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
+  const size_t smem = static_cast<size_t>(kNormBwdWarps + 1) * D * sizeof(float);
+  if (D <= 128) norm_bwd_kernel<TIn, TG, TDx, 1><<<grid, kNormBwdWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
+  else if (D <= 256) norm_bwd_kernel<TIn, TG, TDx, 2><<<grid, kNormBwdWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
+  else if (D <= 512) norm_bwd_kernel<TIn, TG, TDx, 4><<<grid, kNormBwdWarps * 32, smem, stream>>>(xi, gi, w, mean, rstd, dxo, dwp, dbp, M, D, rms, g_res, dx_bf16);
   else return FK_ERR_UNSUPPORTED;
   return FK_OK;
 }
@@ -309,7 +354,7 @@ FK_API int fk_norm_forward(const void* x, int x_dtype, const float* weight, cons
   return FK_OK;
 }
 
-FK_API int fk_norm_backward_grid(void) { return 148 * 4; }
+FK_API int fk_norm_backward_grid(void) { return 148; }
 
 // dweight / dbias = column sums of the per-block partials [nb, D] of fk_norm_backward / fk_add_norm_backward: both in ONE
 // launch, rows added in a fixed order (deterministic).

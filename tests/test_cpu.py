@@ -28,7 +28,7 @@ def test_host_helpers_without_gpu():
     assert L.fk_vq_search_slots(16384, 8192, 148) == 8
     assert L.fk_vq_search_slots(256, 128, 148) == 2
     assert L.fk_vq_finish_partials(17) == 3 and L.fk_masked_l1_partials(16) == 2
-    assert L.fk_norm_backward_grid() == 592
+    assert L.fk_norm_backward_grid() == 148
     if not torch.cuda.is_available():
         assert L.fk_device_ok() == 0
     # argument validation happens before any CUDA call
