@@ -18,12 +18,16 @@ All SoundStream convolutions have dilation 1 (vq_brain.py:48-63 builds every Res
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import gemm
-from ._lib import FkError
+from .ops import column_sum
+from ._lib import FkError, check, lib, ptr, stream
 
 BF16 = torch.bfloat16
+PAD_IMPL = os.environ.get("FK_CONV_PAD", "own")      # "torch": zeros + strided copy (cross-check)
 
 
 def _padded(x3: torch.Tensor, rows_per_trial: int, left: int, slack: int) -> torch.Tensor:
@@ -31,7 +35,16 @@ def _padded(x3: torch.Tensor, rows_per_trial: int, left: int, slack: int) -> tor
     at offset `left`, zeros elsewhere (causal left padding, right padding, and `slack` rows so that the last im2col rows stay
     inside the allocation)."""
     B, T, C = x3.shape
-    buf = torch.zeros(B * rows_per_trial + slack, C, device=x3.device, dtype=BF16)       # (a memset, not a kernel)
+    total = B * rows_per_trial + slack
+    sb, st = (x3.stride(0), x3.stride(1)) if B > 1 else (T * x3.stride(1), x3.stride(1))
+    if (PAD_IMPL == "own" and x3.dtype in (torch.float32, BF16) and C % 8 == 0 and x3.stride(2) == 1 and sb % 8 == 0 and st % 8 == 0
+            and st >= C and x3.data_ptr() % 16 == 0 and B > 0 and T > 0 and x3.device.index == torch.cuda.current_device()):
+        # one pass: zeros and data (fk_pad_rows); the autograd Functions below run on the tensors' device already
+        buf = torch.empty(total, C, device=x3.device, dtype=BF16)
+        check(lib().fk_pad_rows(ptr(x3), 0 if x3.dtype == torch.float32 else 1, B, T, C, sb, st, ptr(buf), rows_per_trial, left,
+                                total, stream()), "fk_pad_rows")
+        return buf
+    buf = torch.zeros(total, C, device=x3.device, dtype=BF16)                            # (a memset, not a kernel)
     buf[:B * rows_per_trial].view(B, rows_per_trial, C)[:, left:left + T] = x3          # one copy, converts to bf16 on the way
     return buf
 
@@ -87,7 +100,7 @@ class _CausalConvFn(torch.autograd.Function):
             dw2 = gemm.gemm_tn(g2, A, name="conv_dw")                  # [Cout, k * Cin]
             dw = dw2.view(Cout, k, Cin).permute(0, 2, 1).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
-            db = g2.sum(0, dtype=torch.float32)                        # (the padded copy is contiguous; its extra rows are zero)
+            db = column_sum(g2)                                        # (the padded copy is contiguous; its extra rows are zero)
         if ctx.needs_input_grad[0]:
             if s == 1:
                 # dx[u] = sum_j' g[u + j'] W_{k-1-j'}: im2col of the right-padded dY, taps reversed
@@ -142,7 +155,7 @@ class _CausalConvTransposeFn(torch.autograd.Function):
             d = d.view(2, Cout, 2, Cin)
             dw = torch.stack([d[0, :, 1].t(), d[1, :, 1].t(), d[0, :, 0].t(), d[1, :, 0].t()], dim=2).to(weight.dtype)    # [Cin, Cout, 4]
         if has_bias and ctx.needs_input_grad[2]:
-            db = g2.sum(0, dtype=torch.float32).view(2, Cout).sum(0)
+            db = column_sum(g2).view(2, Cout).sum(0)
         if ctx.needs_input_grad[0]:
             # dx[v] = [g[2v] | g[2v+1] | g[2v+2] | g[2v+3]] . [W_0 | W_1 | W_2 | W_3]
             Ag = _rows(gbuf, M, 2, 1)

@@ -145,7 +145,8 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = gemm_tn(g2, x2, name="gemm_linear_dw").to(ctx.w_dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = g2.sum(0, dtype=torch.float32).to(ctx.b_dtype)
+            from .ops import column_sum                 # (ops imports nothing from this module at import time)
+            db = column_sum(g2).to(ctx.b_dtype)
         return dx, dw, db
 
 

@@ -17,6 +17,7 @@ _DT = {torch.float32: 0, torch.bfloat16: 1}
 
 import os
 
+COLSUM_IMPL = os.environ.get("FK_COLSUM", "own")        # bias gradients: "own" = fk_colsum_partials, "torch" = g.sum(0, dtype=float32)
 # attention backward implementation: "tc" = tcgen05/TMEM/TMA kernels (attention_tc.cu), "legacy" = mma.sync kernels
 ATTN_BWD_IMPL = os.environ.get("FK_ATTN_BWD", "tc")
 ATTN_FWD_IMPL = os.environ.get("FK_ATTN_FWD", "tc")
@@ -38,6 +39,21 @@ def _reduce_partials(dwp, dbp, w_dtype):
     db = torch.empty(D, device=dwp.device, dtype=torch.float32) if dbp is not None else None
     check(lib().fk_norm_reduce_partials(ptr(dwp), ptr(dbp), nb, D, ptr(dw), ptr(db), stream()), "fk_norm_reduce_partials")
     return dw.to(w_dtype), (db.to(w_dtype) if db is not None else None)
+
+
+def column_sum(g2: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a bf16 [M, N] matrix (bias gradient of a Linear / Conv1d: sum of dY over the tokens), two launches,
+    fixed summation order.  Falls back to torch's reduction for layouts the kernel does not take."""
+    M, N = g2.shape
+    if (COLSUM_IMPL != "own" or g2.dtype != torch.bfloat16 or N % 8 != 0 or g2.stride(1) != 1 or g2.stride(0) % 8 != 0
+            or g2.stride(0) < N or g2.data_ptr() % 16 != 0 or M * N < (1 << 23) or g2.device.index != torch.cuda.current_device()):
+        return g2.sum(0, dtype=torch.float32)          # (below ~8 M elements one torch launch beats two of ours: launch-bound)
+    nb = lib().fk_colsum_grid()
+    part = torch.empty(nb, N, device=g2.device, dtype=torch.float32)
+    out = torch.empty(N, device=g2.device, dtype=torch.float32)
+    check(lib().fk_colsum_partials(ptr(g2), M, N, g2.stride(0), ptr(part), stream()), "fk_colsum_partials")
+    check(lib().fk_norm_reduce_partials(ptr(part), None, nb, N, ptr(out), None, stream()), "fk_norm_reduce_partials")
+    return out
 
 
 class _NormFn(torch.autograd.Function):

@@ -121,6 +121,18 @@ int fk_norm_reduce_partials(const float* dw_part, const float* db_part, int nb, 
 int fk_norm_backward(const void* x, int x_dtype, const void* g, int g_dtype, const float* weight, const float* mean,
                      const float* rstd, void* dx, int dx_dtype, float* dw_part, float* db_part, long long M, int D,
                      int rms, void* stream);
+/* ---- helpers of the implicit-GEMM convolutions (models/vq_brain.py:22-45: F.pad on the time axis; bias gradients) ---- */
+/* out [(total_rows), C] bf16: trial b's T rows at out[b * rows_per_trial + left ...], zeros everywhere else (causal left
+ * padding, right padding, slack rows), in one pass.  x [B, T, C]: f32 (0) or bf16 (1), channels contiguous, strides in
+ * elements (multiples of 8). */
+int fk_pad_rows(const void* x, int x_dtype, long long B, long long T, int C, long long stride_b, long long stride_t,
+                void* out, long long rows_per_trial, long long left, long long total_rows, void* stream);
+/* column sums of a bf16 [M, N] matrix (row stride ld): part [fk_colsum_grid(), N] fp32 per-CTA partials in a fixed order;
+ * reduce them with fk_norm_reduce_partials(part, NULL, fk_colsum_grid(), N, out, NULL).  Bias gradient of nn.Linear /
+ * nn.Conv1d (sum of dY over tokens). */
+int fk_colsum_grid(void);
+int fk_colsum_partials(const void* g, long long M, int N, long long ld, float* part, void* stream);
+
 /* MLP gate silu(w1 x) * (w3 x) (brainformer.py:123-124) on the fused bf16 projection h13 [M, 2H]. */
 int fk_swiglu_forward(const void* h13, void* y, long long M, int H, void* stream);
 int fk_swiglu_backward(const void* h13, const void* gy, void* dh13, long long M, int H, void* stream);

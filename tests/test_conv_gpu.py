@@ -101,3 +101,36 @@ def test_soundstream_stacks_own_convs_match_cudnn_path(monkeypatch):
         assert o.shape == x.shape and torch.isfinite(o.float()).all()
         losses[impl] = float(loss.sum())
     assert abs(losses["own"] - losses["cudnn"]) <= 3e-2 * abs(losses["cudnn"]), losses
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,C,rpt,left,slack,view", [(3, 50, 64, 56, 4, 5, False), (1, 7, 8, 9, 2, 3, False), (4, 33, 128, 40, 0, 2, True),
+                                                       (128, 512, 256, 514, 2, 3, False)])
+def test_pad_rows_bit_exact(dtype, B, T, C, rpt, left, slack, view):
+    """fk_pad_rows == zeros + strided copy (the F.pad of CausalConv1d, models/vq_brain.py:24-27), bit for bit."""
+    from frankenstein_b200 import conv
+    g = torch.Generator().manual_seed(B * 7 + T)
+    if view:        # a row-strided view, as the sliced output of the previous convolution is
+        base = torch.randn(B, T + 5, C, generator=g).cuda().to(dtype)
+        x = base[:, :T]
+    else:
+        x = torch.randn(B, T, C, generator=g).cuda().to(dtype)
+    got = conv._padded(x, rpt, left, slack)
+    ref = torch.zeros(B * rpt + slack, C, device="cuda", dtype=torch.bfloat16)
+    ref[:B * rpt].view(B, rpt, C)[:, left:left + T] = x
+    assert got.shape == ref.shape and got.dtype == torch.bfloat16
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("M,N,ld", [(1000, 64, 64), (5, 256, 256), (70000, 512, 512), (40990, 320, 384), (5000, 4096, 4096), (65536, 1536, 1536)])
+def test_column_sum(M, N, ld):
+    """bias gradient = sum of dY over the tokens: fp32 sums of bf16 data, deterministic (two runs bit-identical)."""
+    from frankenstein_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    full = torch.randn(M, ld, generator=g).cuda().to(torch.bfloat16)
+    g2 = full[:, :N]
+    a, b = ops.column_sum(g2), ops.column_sum(g2)
+    assert torch.equal(a, b)
+    ref = g2.double().sum(0)
+    scale = g2.double().abs().sum(0).max().item()
+    assert (a.double() - ref).abs().max().item() <= 1e-6 * scale
