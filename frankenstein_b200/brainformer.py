@@ -194,7 +194,8 @@ class CausalSelfAttention(nn.Module):
 
 
 class CausalCrossAttention(nn.Module):
-    """models/brainformer.py:175-219 (perceiver resampler; <= 32 queries -> library SDPA)."""
+    """models/brainformer.py:175-219 (perceiver resampler): a few learnable queries against the
+    whole token sequence -> the split-key kernels of csrc/small_attention.cu; dense-mask SDPA only for shapes outside them."""
 
     def __init__(self, config, is_causal=True):
         super().__init__()

@@ -406,10 +406,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
       constexpr uint32_t idesc_score = umma_idesc_bf16(kRows, kCols);
       const int T_u = __shfl_sync(0xffffffffu, T, 0);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint64_t dA = umma_desc_sw64(smem_u32(smem + TcSmem::resA + (item_n & 1) * 16384)),
-                     dB = umma_desc_sw64(smem_u32(smem + TcSmem::resB + (item_n & 1) * 16384));
       const uint32_t stream = smem_u32(smem + TcSmem::stream);
-      (void)dA; (void)dB;
       mbar_wait(res_tmem, item_n & 1);                // the resident tiles of this item sit in TMEM (copied by warpgroup 0)
       tc_fence_after();
       const uint32_t tA = tmem_u + kResCol, tB = tmem_u + kResCol + 16;
@@ -424,7 +421,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
         uint64_t* const bar_full = &sdp_full[g];
         // statistics K step (fold): DKV  A = constant ones tile (keys), B = the tile's query statistics;
         //                           DQ   A = the resident queries' statistics, B = constant ones tile (keys)
-        uint64_t fA_s = 0, fA_d = 0, fB_s = 0, fB_d = 0;
+        uint64_t fB_s = 0, fB_d = 0;
         if constexpr (fold) {
           // B operands of the statistics K step (its A operands are in TMEM): DKV the tile's statistics rows, DQ the ones tiles
           fB_s = fB_d = umma_desc_sw32(stream + stage * 16384 + 8192);
@@ -432,7 +429,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_resA, const __grid_con
             fB_s = umma_desc_sw32(smem_u32(smem + TcSmem::ones));
             fB_d = umma_desc_sw32(smem_u32(smem + TcSmem::ones + 4096));
           }
-          (void)fA_s; (void)fA_d;
           asm volatile("" : "+l"(fB_s), "+l"(fB_d));
         }
         {
