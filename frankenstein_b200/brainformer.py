@@ -214,16 +214,18 @@ class CausalCrossAttention(nn.Module):
         B, T, _ = x.shape
         S = context.shape[1]
         q = _linear_bf16(x, self.qw.weight)
-        # two projections instead of one fused [k|v] GEMM: slicing a fused buffer costs a zero-fill + strided copy per
-        # slice in autograd (select_backward), more than the second GEMM launch
         ctx_bf16 = context.to(BF16)
-        k = _linear_bf16(ctx_bf16, self.kw.weight)
-        v = _linear_bf16(ctx_bf16, self.vw.weight)
         hd = q.shape[-1] // self.n_heads
         if attn_mask is None and x.is_cuda and ops.small_attention_supported(T, hd):
-            # few learnable queries against thousands of context tokens: the split-key kernel of csrc/small_attention.cu
-            res = ops.small_attention(q, k, v, self.n_heads)
+            # few learnable queries against thousands of context tokens: the split-key kernel of csrc/small_attention.cu,
+            # fed by ONE fused k | v projection that it reads in place and whose gradient it writes as one buffer (one pass
+            # over the context per GEMM instead of two, no gradient add of the two context gradients)
+            kv = _linear_bf16(ctx_bf16, torch.cat([self.kw.weight, self.vw.weight], dim=0))
+            res = ops.small_attention_kv(q, kv, self.n_heads)
         else:
+            # two projections: slicing a fused buffer costs a zero-fill + strided copy per slice in autograd (select_backward)
+            k = _linear_bf16(ctx_bf16, self.kw.weight)
+            v = _linear_bf16(ctx_bf16, self.vw.weight)
             q, k, v = (t.view(B, t.shape[1], self.n_heads, -1).transpose(1, 2) for t in (q, k, v))
             res = _dense_mask_attention(q, k, v, attn_mask)
             res = res.transpose(1, 2).reshape(B, T, -1)

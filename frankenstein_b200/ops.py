@@ -511,6 +511,74 @@ class _SmallAttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None, None
 
 
+class _SmallAttnKVFn(torch.autograd.Function):
+    """small_attention on a FUSED key | value projection kv [B, S, 2 * H * hd] (columns [0, W) = k, [W, 2 W) = v): the kernels
+    read the two halves in place through their row strides, and the backward writes dk | dv into ONE buffer of the same
+    layout, so the projection that produced kv gets a single gradient (one dX GEMM, one dW GEMM, no gradient add)."""
+
+    @staticmethod
+    @on_tensor_device
+    def forward(ctx, q, kv, n_heads, scale, rope_table, rope_q0, rope_k0):
+        require_cuda(q, kv)
+        require_device()
+        q, kv = _rows_ok(q), _rows_ok(kv)
+        B, Tq, W = q.shape
+        S = kv.shape[1]
+        H = n_heads
+        hd = W // H
+        if kv.shape != (B, S, 2 * W) or kv.stride(2) != 1:
+            raise FkError(f"small_attention_kv: q {tuple(q.shape)} and kv {tuple(kv.shape)} do not match")
+        if not small_attention_supported(Tq, hd):
+            raise FkError("small_attention serves <= 64 queries at head_dim 16 / 32 / 64")
+        k, v = kv[..., :W], kv[..., W:]
+        dev = q.device
+        nch = lib().fk_small_attn_chunks(S)
+        out = torch.empty(B, Tq, W, device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, H, Tq, device=dev, dtype=torch.float32)
+        part_o = torch.empty(B, H, nch, Tq, hd, device=dev, dtype=torch.float32)
+        part_ml = torch.empty(B, H, nch, Tq, 2, device=dev, dtype=torch.float32)
+        rl = 0 if rope_table is None else rope_table.shape[0]
+        with timed("small_attn_fwd", 4.0 * B * H * Tq * S * hd):
+            check(lib().fk_small_attn_forward(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v),
+                                              v.stride(0), v.stride(1), ptr(out), out.stride(0), out.stride(1), ptr(lse), B, H,
+                                              Tq, S, hd, scale, ptr(rope_table), rl, rope_q0, rope_k0, ptr(part_o),
+                                              ptr(part_ml), stream()), "fk_small_attn_forward")
+        ctx.save_for_backward(q, kv, out, lse)
+        ctx.meta = (H, hd, scale, rope_table, rope_q0, rope_k0, nch)
+        return out
+
+    @staticmethod
+    @on_tensor_device
+    def backward(ctx, g):
+        q, kv, out, lse = ctx.saved_tensors
+        H, hd, scale, rope_table, rope_q0, rope_k0, nch = ctx.meta
+        B, Tq, W = q.shape
+        S = kv.shape[1]
+        g = _rows_ok(g)
+        k, v = kv[..., :W], kv[..., W:]
+        dq = torch.empty_like(q)
+        dkv = torch.empty(B, S, 2 * W, device=kv.device, dtype=kv.dtype)
+        dk, dv = dkv[..., :W], dkv[..., W:]
+        # (q and kv were made dense by _rows_ok in forward, so the fresh gradient buffers share their strides)
+        part_dq = torch.empty(B, H, nch, Tq, hd, device=q.device, dtype=torch.float32)
+        rl = 0 if rope_table is None else rope_table.shape[0]
+        with timed("small_attn_bwd", 10.0 * B * H * Tq * S * hd):
+            check(lib().fk_small_attn_backward(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v),
+                                               v.stride(0), v.stride(1), ptr(out), out.stride(0), out.stride(1), ptr(g),
+                                               g.stride(0), g.stride(1), ptr(lse), ptr(dq), ptr(dk), ptr(dv), B, H, Tq, S, hd,
+                                               scale, ptr(rope_table), rl, rope_q0, rope_k0, ptr(part_dq), stream()),
+                  "fk_small_attn_backward")
+        return dq, dkv, None, None, None, None, None
+
+
+def small_attention_kv(q, kv, n_heads: int, scale: Optional[float] = None):
+    """softmax(q k^T * scale) v with k | v given as one fused projection kv [B, S, 2 * H * hd] (no mask, no RoPE)."""
+    hd = q.shape[-1] // n_heads
+    if not (q.is_cuda and kv.is_cuda):
+        raise FkError("frankenstein_b200 kernels run on a B200 only (no CPU fallback)")
+    return _SmallAttnKVFn.apply(q, kv, n_heads, float(hd ** -0.5 if scale is None else scale), None, 0, 0)
+
+
 def small_attention(q, k, v, n_heads: int, scale: Optional[float] = None, rope: Optional[RopeSpec] = None,
                     rope_q0: Optional[int] = None, rope_k0: Optional[int] = None):
     """softmax(q k^T * scale) v for few queries: q [B, Tq <= 64, H*hd], k / v [B, S, H*hd] -> [B, Tq, H*hd] bf16 (no mask).

@@ -107,3 +107,25 @@ def test_perceiver_gradients_match_fp32_modules():
     assert g1.keys() == g2.keys() and len(g1) > 10
     for n in g1:
         _close(g1[n], g2[n], 6e-2, f"perceiver grad {n}")
+
+
+@pytest.mark.parametrize("B,H,hd,Tq,S", [(2, 4, 16, 32, 4096), (3, 2, 16, 25, 300), (1, 4, 32, 64, 1000)])
+def test_small_attention_fused_kv_equals_separate(B, H, hd, Tq, S):
+    """k | v as ONE projection buffer read in place (CausalCrossAttention's fused projection): bit-identical to the
+    separate-operand call, forward and gradients (d kv = [dk | dv])."""
+    from frankenstein_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + S)
+    W = H * hd
+    q = (torch.randn(B, Tq, W, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    kv = torch.randn(B, S, 2 * W, generator=g).to(torch.bfloat16).cuda()
+    w = torch.randn(B, Tq, W, generator=g).to(torch.bfloat16).cuda()
+    qa, kva = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    oa = ops.small_attention_kv(qa, kva, H)
+    oa.backward(w)
+    qb = q.clone().requires_grad_(True)
+    kb, vb = kv[..., :W].contiguous().requires_grad_(True), kv[..., W:].contiguous().requires_grad_(True)
+    ob = ops.small_attention(qb, kb, vb, H)
+    ob.backward(w)
+    assert torch.equal(oa, ob)
+    assert torch.equal(qa.grad, qb.grad)
+    assert torch.equal(kva.grad[..., :W], kb.grad) and torch.equal(kva.grad[..., W:], vb.grad)
