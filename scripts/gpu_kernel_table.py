@@ -193,6 +193,16 @@ def main():
     pre = rnd(128, 32, 768)
     report("prefix_embed_fwd (32 prefix + 25 tokens, n_embd 768, 128 trials)", lambda: prefix.prefix_embed(wte, wpe, idx, pre),
            bytes_=128 * 57 * 768 * 4 * 2 + 57 * 768 * 4, note="includes the fp32 copies of wte / wpe the wrapper makes (no-ops for fp32 parameters)")
+    # ---- convolution helpers (cfg-4 SoundStream activations: 128 trials x 512 bins x 256 channels) ----
+    from frankenstein_b200 import conv
+    xa = rnd(128, 512, 256, dtype=torch.bfloat16)
+    report("pad_rows (causal left pad k - 1 = 2, [128, 512, 256] bf16 -> padded signal)", lambda: conv._padded(xa, 514, 2, 3),
+           bytes_=128 * 512 * 256 * 2 + (128 * 514 + 3) * 256 * 2)
+    gy = rnd(128 * 514, 256, dtype=torch.bfloat16)
+    report("colsum_partials + reduce (bias gradient of a convolution, [65792, 256] bf16)", lambda: ops.column_sum(gy),
+           bytes_=128 * 514 * 256 * 2)
+    gl = rnd(M, 512, dtype=torch.bfloat16)
+    report("colsum_partials + reduce (bias gradient of a Linear, [M, 512] bf16)", lambda: ops.column_sum(gl), bytes_=M * 512 * 2)
 
 
 if __name__ == "__main__":
