@@ -98,7 +98,7 @@ class _CausalConvFn(torch.autograd.Function):
         dw = db = dx = None
         if ctx.needs_input_grad[1]:
             dw2 = gemm.gemm_tn(g2, A, name="conv_dw")                  # [Cout, k * Cin]
-            dw = dw2.view(Cout, k, Cin).permute(0, 2, 1).to(weight.dtype)
+            dw = dw2.view(Cout, k, Cin).permute(0, 2, 1).to(weight.dtype).contiguous()        # (dense, as DDP's bucket views expect)
         if has_bias and ctx.needs_input_grad[2]:
             db = column_sum(g2)                                        # (the padded copy is contiguous; its extra rows are zero)
         if ctx.needs_input_grad[0]:
@@ -153,7 +153,7 @@ class _CausalConvTransposeFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             d = gemm.gemm_tn(g2, A, name="convT_dw")                    # [2 Cout, 2 Cin]: block (p, tap), tap 0 <-> W_{p+2}, tap 1 <-> W_p
             d = d.view(2, Cout, 2, Cin)
-            dw = torch.stack([d[0, :, 1].t(), d[1, :, 1].t(), d[0, :, 0].t(), d[1, :, 0].t()], dim=2).to(weight.dtype)    # [Cin, Cout, 4]
+            dw = torch.stack([d[0, :, 1].t(), d[1, :, 1].t(), d[0, :, 0].t(), d[1, :, 0].t()], dim=2).to(weight.dtype)    # [Cin, Cout, 4] (dense)
         if has_bias and ctx.needs_input_grad[2]:
             db = column_sum(g2).view(2, Cout).sum(0)
         if ctx.needs_input_grad[0]:
